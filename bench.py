@@ -1,0 +1,319 @@
+#!/usr/bin/env python
+"""Benchmark of the projection hot path (FP3D + BP3D) on B200.
+
+Contract: ``python bench.py --gpus N --steps K --warmup W`` prints ONE JSON line.
+
+* workload   BASELINE.json configs[2]: cone_vec 512^3 volume, 720 angles,
+             512 x 768 detector (SURVEY.md 8d cfg 3).  A "step" is one forward
+             projection followed by one backprojection of the whole problem.
+* metric     GUPS = voxels x angles / second / 1e9, summed over FP and BP.
+* value      device-resident inputs, CUDA-event timed.
+* e2e        the same step through the public operator API with pinned HOST
+             arrays (H2D + kernels + D2H inside the timed region).
+* roofline   for the dominant kernel: algorithmic bytes 4*(vol + proj) per
+             launch over its measured duration, against the measured HBM peak;
+             `interp` adds the in-SM interpolation view (updates/clk/SM).
+* cpu_baseline / --impl reference: the CPU restatement (oracle/, fp32,
+             OpenMP, all host cores) on a bounded sample of the same workload.
+             ASTRA -- the reference's engine -- has no CPU 3-D projector and is
+             not installable here, so the port is the CPU arm.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "FP3D+BP3D GUPS (voxels x angles / s), cone_vec 512^3 x 720 angles"
+UNIT = "GUPS"
+
+
+def workload(n=512, n_angles=720):
+    """cfg 3 geometry as ASTRA-style vectors."""
+    from oracle import oracle as O  # geometry helper only (restated geom_2vec)
+
+    det = (n, 3 * n // 2)
+    ang = np.linspace(0, 2 * np.pi, n_angles, endpoint=False)
+    vec = O.cone_vectors(ang, 2.8125 / det[1], 1.875 / det[0], 4.0, 2.0)
+    window = [(-0.5, 0.5)] * 3
+    return dict(kind=0, vol_shape=(n, n, n), window=window, det_shape=det, vectors=vec)
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f), "measured"
+    return {"hbm_gbs": 6650.0, "sm_max_mhz": 1965.0}, "fallback"
+
+
+class ClockSampler:
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index = index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [x.strip() for x in s.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def cpu_sample(n=192, n_angles=96, repeats=1):
+    """Bounded CPU sample of the same workload: (n^3, n_angles, n x 1.5n)."""
+    from oracle import oracle as O
+
+    w = workload(n, n_angles)
+    Q = O.OracleProjector(w["kind"], w["vol_shape"], [a for a, _ in w["window"]], [b for _, b in w["window"]],
+                          w["det_shape"], w["vectors"])
+    x = O.hollow_box(n)
+    y = np.zeros(Q.proj_shape, np.float32)
+    xb = np.zeros(Q.vol_shape, np.float32)
+    Q.fp(x, out=y, dtype=np.float32)  # warm caches / thread pool
+    t0 = time.perf_counter()
+    for _ in range(repeats):
+        Q.fp(x, out=y, dtype=np.float32)
+        Q.bp(y, out=xb, dtype=np.float32)
+    dt = (time.perf_counter() - t0) / repeats
+    updates = 2.0 * n ** 3 * n_angles
+    return updates / dt / 1e9, dt, f"cone {n}^3 x {n_angles} angles x {n}x{3 * n // 2} det, FP+BP, fp32 OpenMP port"
+
+
+def run_reference(args):
+    """--impl reference: the CPU port on all host cores (rank 0 only)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    for _ in range(args.warmup):
+        cpu_sample(96, 48)
+    vals, ms = [], []
+    for _ in range(args.steps):
+        g, dt, sample = cpu_sample()
+        vals.append(g); ms.append(dt * 1e3)
+    v = float(np.mean(vals))
+    w = workload()
+    line = {
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cone_vec 512^3 vol, 720 angles, 512x768 det, FP+BP per step (bounded CPU sample)",
+                   "note": "ASTRA (the reference engine) is CUDA-only and absent; CPU port of the same arithmetic"},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    from tomosipo_b200 import _backend as B
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: tomosipo_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    w = workload()
+    n = w["vol_shape"][0]
+    n_angles = w["vectors"].shape[0]
+    # N > 1: angle-sharded FP (replicated volume), angle-sharded BP + reduce-scatter
+    a_lo, a_hi = rank * n_angles // world, (rank + 1) * n_angles // world
+    vec = w["vectors"][a_lo:a_hi]
+    P = B.Projector(w["kind"], w["vol_shape"], w["window"], w["det_shape"], vec)
+    from oracle import oracle as O
+    x = torch.from_numpy(O.hollow_box(n)).to(dev)
+    y = torch.empty(P.proj_shape, device=dev, dtype=torch.float32)
+    xb = torch.empty(P.vol_shape, device=dev, dtype=torch.float32)
+    xs = torch.empty((n // world,) + tuple(P.vol_shape[1:]), device=dev) if world > 1 else None
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        P.project(B.FP, False, x.data_ptr(), y.data_ptr(), B.MEM_DEVICE, local, stream)
+        P.project(B.BP, False, xb.data_ptr(), y.data_ptr(), B.MEM_DEVICE, local, stream)
+        if world > 1:
+            dist.reduce_scatter_tensor(xs, xb)      # partial volumes -> z-slabs
+            dist.all_gather_into_tensor(xb, xs)     # z-slabs -> replicated volume for the next FP
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    # per-call timings for the roofline (FP call / BP call), same stream
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    launches0 = P.info().kernel_launches
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t_begin = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+    t_begin.record()
+    for i in range(args.steps):
+        ev[i][0].record()
+        P.project(B.FP, False, x.data_ptr(), y.data_ptr(), B.MEM_DEVICE, local, stream)
+        ev[i][1].record()
+        P.project(B.BP, False, xb.data_ptr(), y.data_ptr(), B.MEM_DEVICE, local, stream)
+        ev[i][2].record()
+        if world > 1:
+            dist.reduce_scatter_tensor(xs, xb)
+            dist.all_gather_into_tensor(xb, xs)
+    t_end.record()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = t_begin.elapsed_time(t_end)
+    if world > 1:
+        t = torch.tensor([total_ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    launches = P.info().kernel_launches - launches0
+    fp_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
+    bp_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
+
+    updates_step = 2.0 * n ** 3 * n_angles  # whole job, FP + BP
+    value = updates_step * args.steps / (total_ms * 1e-3) / 1e9
+
+    # ---- end-to-end through the host-array path (pinned host buffers)
+    xh = torch.from_numpy(O.hollow_box(n)).pin_memory()
+    yh = torch.empty(P.proj_shape, dtype=torch.float32).pin_memory()
+    xbh = torch.empty(P.vol_shape, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        P.project(B.FP, False, xh.data_ptr(), yh.data_ptr(), B.MEM_HOST, local, stream)
+        P.project(B.BP, False, xbh.data_ptr(), yh.data_ptr(), B.MEM_HOST, local, stream)
+        return float(xbh[n // 2, n // 2, n // 2])
+
+    e2e_steps = max(1, min(args.steps, 3))
+    e2e_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = updates_step * e2e_steps / e2e_s / 1e9
+    nvox, npix = x.numel(), y.numel()
+    h2d = 4 * (nvox + npix) * world   # FP: volume in; BP: projections in
+    d2h = 4 * (npix + nvox) * world   # FP: projections out; BP: volume out
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks, peak_kind = load_peaks()
+    b_alg = 4.0 * (nvox + npix)  # bytes per FP or per BP launch (SET mode), SURVEY.md 8d
+    dom = "bp_kernel" if bp_ms >= fp_ms else "fp_kernel"
+    dom_ms = max(bp_ms, fp_ms)
+    achieved = b_alg / (dom_ms * 1e-3) / 1e9
+    sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
+    upd = float(n) ** 3 * (a_hi - a_lo)
+    interp = {
+        "fp_gups": upd / (fp_ms * 1e-3) / 1e9, "bp_gups": upd / (bp_ms * 1e-3) / 1e9,
+        "fp_updates_per_clk_per_sm": upd / (fp_ms * 1e-3) / (sm_mhz * 1e6) / 148,
+        "bp_updates_per_clk_per_sm": upd / (bp_ms * 1e-3) / (sm_mhz * 1e6) / 148,
+        "ceiling_updates_per_clk_per_sm": 8.0,
+        "ceiling_note": "shared-memory gather: 32 words/clk/SM / 4 taps (SURVEY.md 8d planning figure)",
+    }
+    cpu_gups, cpu_dt, sample = cpu_sample()
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "cone_vec 512^3 vol, 720 angles, 512x768 det (BASELINE configs[2]), FP+BP per step",
+                   "phantom": "hollow_box", "l2": "inputs (537 MB + 1132 MB) larger than L2",
+                   "parallelism": "single GPU" if world == 1 else
+                   f"angle-sharded x{world}: FP on replicated volume, BP partial volumes -> NCCL reduce_scatter + all_gather"},
+        "fp_ms": fp_ms, "bp_ms": bp_ms,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+                     "algorithmic_bytes_per_launch": b_alg, "interp": interp},
+        "cpu_baseline": {"value": cpu_gups, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

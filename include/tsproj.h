@@ -1,0 +1,130 @@
+/*
+ * tsproj.h -- C ABI of libtsproj.so, the B200-native (sm_100a) 3D tomographic
+ * projector that replaces the ASTRA calls behind tomosipo's projection path.
+ *
+ * Each entry point names the reference interface it replaces
+ * (paths relative to the reference checkout of ahendriksen/tomosipo v0.6.0).
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative tsp_status; the
+ *     message of the last failure on the calling thread is tsp_last_error().
+ *   - volumes are dense float32 [nz][ny][nx]; projections are dense float32
+ *     [det_rows][n_angles][det_cols]  (tomosipo/links/base.py:21-31).
+ *   - the library never allocates or frees caller buffers.
+ *   - TSP_MEM_DEVICE calls are asynchronous on the given CUDA stream;
+ *     TSP_MEM_HOST calls return after the result is back in host memory
+ *     (ASTRA's synchronous contract, tomosipo/astra.py:146-153).
+ *   - there is no CPU fallback: without a usable CUDA device every compute
+ *     entry point fails with TSP_ERR_CUDA.
+ */
+#ifndef TSPROJ_H
+#define TSPROJ_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TSP_VERSION 100
+
+typedef enum {
+    TSP_OK = 0,
+    TSP_ERR_INVALID = -1, /* bad argument / geometry: maps to ValueError */
+    TSP_ERR_CUDA = -2,    /* CUDA runtime failure: maps to RuntimeError */
+    TSP_ERR_NOMEM = -3
+} tsp_status;
+
+enum { TSP_KIND_CONE_VEC = 0, TSP_KIND_PARALLEL_VEC = 1 };
+enum { TSP_FP = 0, TSP_BP = 1 };
+enum { TSP_MEM_HOST = 0, TSP_MEM_DEVICE = 1 };
+
+/*
+ * The two dicts tomosipo hands to astra.create_projector("cuda3d", pg, vg,
+ * options) (tomosipo/astra.py:90-98), flattened:
+ *   vg  = VolumeGeometry.to_astra()        tomosipo/geometry/volume.py:286-301
+ *         GridColCount = nx, GridRowCount = ny, GridSliceCount = nz,
+ *         option.WindowMin/Max{X,Y,Z} = win_min / win_max (x, y, z order)
+ *   pg  = {Cone,Parallel}VectorGeometry.to_astra()
+ *         tomosipo/geometry/cone_vec.py:174-191, parallel_vec.py:175-192
+ *         Vectors[a] = [src|ray (3), det centre (3), det_u (3), det_v (3)],
+ *         each triple in ASTRA (x, y, z) order; DetectorRowCount = det_rows,
+ *         DetectorColCount = det_cols.
+ *   options = {VoxelSuperSampling, DetectorSuperSampling}.
+ * Circular 'cone' / 'parallel3d' dicts are converted to vectors by the caller
+ * (astra.geom_2vec semantics; see tomosipo_b200/astra_compat.py).
+ * The library copies everything it needs; the caller keeps ownership.
+ */
+typedef struct tsp_geometry {
+    int32_t kind;
+    int32_t nx, ny, nz;
+    double win_min[3];
+    double win_max[3];
+    int32_t det_rows, det_cols, n_angles;
+    const double *vectors; /* n_angles x 12 */
+    int32_t voxel_supersampling, detector_supersampling;
+} tsp_geometry;
+
+typedef struct tsp_projector tsp_projector;
+
+/* Replaces astra.create_projector("cuda3d", ...)  tomosipo/astra.py:90-98.
+ * Host-only; no CUDA call is made until the first tsp_project. */
+int tsp_projector_create(const tsp_geometry *geometry, tsp_projector **out);
+
+/* The reference never frees projector ids (tomosipo/Operator.py:167-172);
+ * this library lets the owner do so. */
+void tsp_projector_destroy(tsp_projector *projector);
+
+/*
+ * Replaces astra.experimental.direct_FPBP3D(projector, vol, proj, mode, "FP"|"BP")
+ * (tomosipo/astra.py:147-153).
+ *   direction   TSP_FP: proj (+)= A vol;  TSP_BP: vol (+)= A^T proj
+ *   additive    0 = MODE_SET (overwrite), 1 = MODE_ADD      astra.py:132-135
+ *   vol, proj   float32; `batch` consecutive dense volumes / projection
+ *               stacks (batch == 1 is the reference behaviour; batch > 1
+ *               serves the leading-dimension loop of
+ *               tomosipo/torch_support.py:49-53,70-74 in one call)
+ *   memory_kind TSP_MEM_HOST  (numpy / CPU tensors; ASTRA's ndarray path) or
+ *               TSP_MEM_DEVICE (astra.data3d.GPULink(ptr, x, y, z, pitch = 4x),
+ *               tomosipo/links/torch.py:94-106)
+ *   device      CUDA device ordinal owning the pointers (links/torch.py:150-152);
+ *               for TSP_MEM_HOST the device to compute on
+ *   cuda_stream cudaStream_t to launch on; NULL = legacy default stream
+ */
+int tsp_project(tsp_projector *projector, int direction, int additive, void *vol, void *proj,
+                int batch, int memory_kind, int device, void *cuda_stream);
+
+/* Introspection used by the tests and by bench.py. */
+typedef struct tsp_projector_info {
+    int32_t n_angles;
+    int32_t n_march_x, n_march_y, n_march_z; /* FP marching-axis census */
+    double voxel_size[3];                     /* x, y, z */
+    int64_t kernel_launches;                  /* kernels launched so far by this projector */
+    int32_t bp_uses_tma;                      /* last BP used TMA-staged footprints */
+    int32_t fp_uses_transpose;                /* last FP built an (x<->y) transposed volume */
+} tsp_projector_info;
+int tsp_projector_get_info(const tsp_projector *projector, tsp_projector_info *info);
+
+/* Per-angle FP marching axis (0 = x, 1 = y, 2 = z), for parity checks. */
+int tsp_projector_marching_axes(const tsp_projector *projector, int32_t *axes);
+
+/* Replaces astra.use_cuda()  (reference tests/__init__.py:7). */
+int tsp_cuda_available(void);
+int tsp_device_count(void);
+int tsp_version(void);
+const char *tsp_last_error(void);
+
+/*
+ * Fused SIRT iteration on device-resident data (the
+ * loop of notebooks/sirt_benchmark.py:130-136):
+ *     y_tmp = R * (A x - y);   x -= C * A^T y_tmp
+ * x, C: [nz][ny][nx];  y, R, y_tmp: [det_rows][n_angles][det_cols].
+ * Runs `iterations` iterations asynchronously on the stream.
+ */
+int tsp_sirt(tsp_projector *projector, void *x, const void *y, const void *R, const void *C,
+             void *y_tmp, int iterations, int device, void *cuda_stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TSPROJ_H */

@@ -1,0 +1,202 @@
+"""ctypes binding of ``libtsproj.so`` (C ABI: ``include/tsproj.h``).
+
+This is the process-internal FFI boundary that replaces the Cython calls
+``astra.create_projector`` / ``astra.experimental.direct_FPBP3D`` of the
+reference (``tomosipo/astra.py:90-98,147-153``).  There is no CPU fallback:
+if the library is missing, or no CUDA device is usable, projection raises.
+"""
+import ctypes
+import os
+import subprocess
+import threading
+
+import numpy as np
+
+_PKG_DIR = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG_DIR, "libtsproj.so")
+CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
+
+KIND_CONE_VEC = 0
+KIND_PARALLEL_VEC = 1
+FP, BP = 0, 1
+MEM_HOST, MEM_DEVICE = 0, 1
+
+ERR_INVALID = -1
+ERR_CUDA = -2
+ERR_NOMEM = -3
+
+
+class tsp_geometry(ctypes.Structure):
+    _fields_ = [
+        ("kind", ctypes.c_int32),
+        ("nx", ctypes.c_int32),
+        ("ny", ctypes.c_int32),
+        ("nz", ctypes.c_int32),
+        ("win_min", ctypes.c_double * 3),
+        ("win_max", ctypes.c_double * 3),
+        ("det_rows", ctypes.c_int32),
+        ("det_cols", ctypes.c_int32),
+        ("n_angles", ctypes.c_int32),
+        ("vectors", ctypes.POINTER(ctypes.c_double)),
+        ("voxel_supersampling", ctypes.c_int32),
+        ("detector_supersampling", ctypes.c_int32),
+    ]
+
+
+class tsp_projector_info(ctypes.Structure):
+    _fields_ = [
+        ("n_angles", ctypes.c_int32),
+        ("n_march_x", ctypes.c_int32),
+        ("n_march_y", ctypes.c_int32),
+        ("n_march_z", ctypes.c_int32),
+        ("voxel_size", ctypes.c_double * 3),
+        ("kernel_launches", ctypes.c_int64),
+        ("bp_uses_tma", ctypes.c_int32),
+        ("fp_uses_transpose", ctypes.c_int32),
+    ]
+
+
+#: every symbol include/tsproj.h declares
+EXPORTED_SYMBOLS = (
+    "tsp_projector_create",
+    "tsp_projector_destroy",
+    "tsp_project",
+    "tsp_projector_get_info",
+    "tsp_projector_marching_axes",
+    "tsp_cuda_available",
+    "tsp_device_count",
+    "tsp_version",
+    "tsp_last_error",
+    "tsp_sirt",
+)
+
+
+def build(force=False, verbose=False):
+    """Compile ``libtsproj.so`` in-tree with nvcc for sm_100a."""
+    cmd = ["make", "-C", CSRC_DIR] + (["-B"] if force else [])
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or res.returncode != 0:
+        print(res.stdout)
+        print(res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError("building libtsproj.so failed")
+    return LIB_PATH
+
+
+_lib = None
+_lock = threading.Lock()
+
+
+def lib():
+    """Load the shared library (once).  Raises ``ImportError`` if absent."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(
+                f"{LIB_PATH} not found. Build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C tomosipo_b200/csrc`. tomosipo_b200 has no CPU fallback."
+            )
+        L = ctypes.CDLL(LIB_PATH)
+        vp = ctypes.c_void_p
+        L.tsp_projector_create.argtypes = [ctypes.POINTER(tsp_geometry), ctypes.POINTER(vp)]
+        L.tsp_projector_create.restype = ctypes.c_int
+        L.tsp_projector_destroy.argtypes = [vp]
+        L.tsp_projector_destroy.restype = None
+        L.tsp_project.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_int,
+                                  ctypes.c_int, vp]
+        L.tsp_project.restype = ctypes.c_int
+        L.tsp_projector_get_info.argtypes = [vp, ctypes.POINTER(tsp_projector_info)]
+        L.tsp_projector_get_info.restype = ctypes.c_int
+        L.tsp_projector_marching_axes.argtypes = [vp, ctypes.POINTER(ctypes.c_int32)]
+        L.tsp_projector_marching_axes.restype = ctypes.c_int
+        L.tsp_cuda_available.restype = ctypes.c_int
+        L.tsp_device_count.restype = ctypes.c_int
+        L.tsp_version.restype = ctypes.c_int
+        L.tsp_last_error.restype = ctypes.c_char_p
+        L.tsp_sirt.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp]
+        L.tsp_sirt.restype = ctypes.c_int
+        _lib = L
+        return _lib
+
+
+def _check(rc):
+    if rc == 0:
+        return
+    msg = lib().tsp_last_error().decode("utf-8", "replace")
+    if rc == ERR_INVALID:
+        raise ValueError(msg)
+    if rc == ERR_NOMEM:
+        raise MemoryError(msg)
+    raise RuntimeError(msg)
+
+
+def cuda_available():
+    """Replacement of ``astra.use_cuda()`` (reference ``tests/__init__.py:7``)."""
+    try:
+        return bool(lib().tsp_cuda_available())
+    except (ImportError, OSError):
+        return False
+
+
+class Projector:
+    """Owner of one ``tsp_projector`` handle.
+
+    ``vectors`` are ASTRA 12-column rows in (x, y, z) order, ``window`` is
+    ((minx, maxx), (miny, maxy), (minz, maxz)) -- exactly the content of the
+    dicts ``create_astra_projector`` builds in the reference.
+    """
+
+    def __init__(self, kind, vol_shape_zyx, window_xyz, det_shape_vu, vectors,
+                 voxel_supersampling=1, detector_supersampling=1):
+        vec = np.ascontiguousarray(vectors, dtype=np.float64)
+        if vec.ndim != 2 or vec.shape[1] != 12:
+            raise ValueError(f"Expected vectors of shape (num_angles, 12). Got {vec.shape}")
+        g = tsp_geometry()
+        g.kind = int(kind)
+        g.nz, g.ny, g.nx = (int(s) for s in vol_shape_zyx)
+        for i in range(3):
+            g.win_min[i] = float(window_xyz[i][0])
+            g.win_max[i] = float(window_xyz[i][1])
+        g.det_rows, g.det_cols = int(det_shape_vu[0]), int(det_shape_vu[1])
+        g.n_angles = vec.shape[0]
+        g.vectors = vec.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        g.voxel_supersampling = int(voxel_supersampling)
+        g.detector_supersampling = int(detector_supersampling)
+        handle = ctypes.c_void_p()
+        _check(lib().tsp_projector_create(ctypes.byref(g), ctypes.byref(handle)))
+        self._handle = handle
+        self.kind = int(kind)
+        self.vol_shape = (g.nz, g.ny, g.nx)
+        self.proj_shape = (g.det_rows, g.n_angles, g.det_cols)
+        self.n_angles = g.n_angles
+
+    def __del__(self):
+        h, self._handle = getattr(self, "_handle", None), None
+        if h is not None and _lib is not None:
+            try:
+                _lib.tsp_projector_destroy(h)
+            except Exception:  # interpreter shutdown
+                pass
+
+    def project(self, direction, additive, vol_ptr, proj_ptr, memory_kind, device=0, stream=0, batch=1):
+        """Raw call: pointers are integers (host or device addresses)."""
+        _check(lib().tsp_project(self._handle, int(direction), int(bool(additive)), ctypes.c_void_p(vol_ptr),
+                                 ctypes.c_void_p(proj_ptr), int(batch), int(memory_kind), int(device),
+                                 ctypes.c_void_p(stream)))
+
+    def sirt(self, x_ptr, y_ptr, r_ptr, c_ptr, ytmp_ptr, iterations, device=0, stream=0):
+        vp = ctypes.c_void_p
+        _check(lib().tsp_sirt(self._handle, vp(x_ptr), vp(y_ptr), vp(r_ptr), vp(c_ptr), vp(ytmp_ptr),
+                              int(iterations), int(device), vp(stream)))
+
+    def info(self):
+        info = tsp_projector_info()
+        _check(lib().tsp_projector_get_info(self._handle, ctypes.byref(info)))
+        return info
+
+    def marching_axes(self):
+        axes = np.zeros(self.n_angles, dtype=np.int32)
+        _check(lib().tsp_projector_marching_axes(self._handle, axes.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
+        return axes

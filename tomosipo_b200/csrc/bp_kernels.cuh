@@ -1,0 +1,321 @@
+// Backprojection: voxel-driven, bilinear detector interpolation, ray-density
+// weight (semantics: SURVEY.md B.2; call site tomosipo/astra.py:147-153).
+//
+// A CTA owns a BP_TX x BP_TY x BP_ZPT voxel tile and loops over *all* angles,
+// so each voxel is written exactly once (ASTRA: one launch per 32 angles, each
+// read-modify-writing the volume).  Per angle batch the detector footprint of
+// the tile is staged into shared memory (zero-filled outside the detector,
+// which is ASTRA's border mode) and sampled with full-precision fp32 weights
+// in tile-local coordinates: the per-(tile, angle) affine maps are re-centred
+// on the tile in fp64 by a few set-up threads, which keeps the fractional
+// weights accurate to ~1e-6 irrespective of detector size.
+#pragma once
+#include "tsp_internal.h"
+
+namespace tsp {
+
+constexpr int BP_TX = 32;   // voxels along x per CTA (= warp width)
+constexpr int BP_TY = 8;    // voxels along y per CTA
+constexpr int BP_ZPT = 8;   // z voxels per thread (registers)
+constexpr int BP_K = 8;     // angles staged per batch
+constexpr int BP_WU = 64;   // staged footprint: max columns
+constexpr int BP_WV = 22;   // staged footprint: max rows
+constexpr int BP_PITCH = BP_WU + 1;
+constexpr int BP_THREADS = BP_TX * BP_TY;
+
+// BP_SMEM_CLAMP: the footprint was clipped to the detector (+4 pixel zero margin), so
+// buffer coordinates are clamped into the zero margin before sampling.
+enum { BP_SKIP = 0, BP_SMEM = 1, BP_GLOBAL = 2, BP_SMEM_CLAMP = 3 };
+
+struct BPArgs {
+    const float *proj;
+    float *vol;
+    int nx, ny, nz;
+    int det_u, det_v, n_angles;
+    const BPAngle *angles;
+    float out_scale;  // voxel volume
+    int additive;
+    int vox_ss;
+};
+
+// Per-(tile, angle) set-up result, tile-local: for a voxel at offset
+// (dx, dy, dz) from the tile centre,
+//   column = (Bu + Au.d) / (Bd + Ad.d),   row = (Bv + Av.d) / (Bd + Ad.d)
+// are *buffer* coordinates (BP_SMEM) or detector index coordinates (BP_GLOBAL).
+struct BPLocal {
+    float au[3], bu;
+    float av[3], bv;
+    float ad[3], bd;
+    int u_lo, v_lo, wu, wv;
+    int mode;
+    float weight;
+};
+
+__device__ __forceinline__ float bp_sample_global(const float *__restrict__ proj, int det_u, int det_v,
+                                                  size_t row_pitch, float fu, float fv)
+{
+    if (!(fu > -1.0f && fu < (float)det_u && fv > -1.0f && fv < (float)det_v)) return 0.0f;
+    const float flu = floorf(fu), flv = floorf(fv);
+    const int iu = (int)flu, iv = (int)flv;
+    const float wu = fu - flu, wv = fv - flv;
+    const bool u0 = iu >= 0, u1 = iu + 1 < det_u, v0 = iv >= 0, v1 = iv + 1 < det_v;
+    const float *s = proj + (long long)iv * (long long)row_pitch + iu;
+    const float p00 = (u0 && v0) ? __ldg(s) : 0.0f;
+    const float p10 = (u1 && v0) ? __ldg(s + 1) : 0.0f;
+    const float p01 = (u0 && v1) ? __ldg(s + row_pitch) : 0.0f;
+    const float p11 = (u1 && v1) ? __ldg(s + row_pitch + 1) : 0.0f;
+    const float lo = fmaf(wu, p10 - p00, p00);
+    const float hi = fmaf(wu, p11 - p01, p01);
+    return fmaf(wv, hi - lo, lo);
+}
+
+// Eight threads per angle: each projects one corner of the tile's voxel-centre
+// box; shuffles reduce the bounding box; lane 0 writes the local map.
+__device__ __forceinline__ void bp_setup(const BPArgs &P, const BPAngle *__restrict__ ang, int corner,
+                                         double xc, double yc, double zc, double hx, double hy,
+                                         double hz, BPLocal *out)
+{
+    const double den_c = ang->dn[0] * xc + ang->dn[1] * yc + ang->dn[2] * zc + ang->dn[3];
+    const double nu_c = ang->nu[0] * xc + ang->nu[1] * yc + ang->nu[2] * zc + ang->nu[3];
+    const double nv_c = ang->nv[0] * xc + ang->nv[1] * yc + ang->nv[2] * zc + ang->nv[3];
+    const double dx = (corner & 1) ? hx : -hx;
+    const double dy = (corner & 2) ? hy : -hy;
+    const double dz = (corner & 4) ? hz : -hz;
+    const double den = den_c + ang->dn[0] * dx + ang->dn[1] * dy + ang->dn[2] * dz;
+    const double uu = (nu_c + ang->nu[0] * dx + ang->nu[1] * dy + ang->nu[2] * dz) / den;
+    const double vv = (nv_c + ang->nv[0] * dx + ang->nv[1] * dy + ang->nv[2] * dz) / den;
+    double umin = uu, umax = uu, vmin = vv, vmax = vv, dmin = den, dmax = den;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        umin = fmin(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+        umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+        vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+        dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    }
+    if (corner != 0) return;
+
+    BPLocal L;
+    int mode = BP_SMEM;
+    // The projective map is monotone over the box only if den keeps its sign.
+    const bool regular = (dmin > 0.0 || dmax < 0.0) && isfinite(umin) && isfinite(umax) &&
+                         isfinite(vmin) && isfinite(vmax) &&
+                         fmin(fabs(dmin), fabs(dmax)) > 1e-6 * fmax(fabs(dmin), fabs(dmax));
+    double off_u = 0.5, off_v = 0.5;  // texel-centre convention -> index coordinates
+    int u_lo = 0, v_lo = 0, wu = 0, wv = 0;
+    if (!regular) {
+        mode = BP_GLOBAL;
+    } else {
+        const double cu0 = -4.0, cv0 = -4.0, cu1 = (double)P.det_u + 4.0, cv1 = (double)P.det_v + 4.0;
+        if (umin < cu0 || vmin < cv0 || umax > cu1 || vmax > cv1) mode = BP_SMEM_CLAMP;
+        umin = fmax(umin, cu0); vmin = fmax(vmin, cv0);
+        umax = fmin(umax, cu1); vmax = fmin(vmax, cv1);
+        if (umax < umin || vmax < vmin) {
+            mode = BP_SKIP;  // footprint entirely off the detector
+        } else {
+            u_lo = (int)floor(umin - 0.5) - 1;
+            v_lo = (int)floor(vmin - 0.5) - 1;
+            wu = (int)floor(umax - 0.5) + 3 - u_lo;
+            wv = (int)floor(vmax - 0.5) + 3 - v_lo;
+            if (wu > BP_WU || wv > BP_WV) {
+                mode = BP_GLOBAL;
+            } else {
+                off_u += (double)u_lo;
+                off_v += (double)v_lo;
+            }
+        }
+    }
+    L.au[0] = (float)(ang->nu[0] - off_u * ang->dn[0]);
+    L.au[1] = (float)(ang->nu[1] - off_u * ang->dn[1]);
+    L.au[2] = (float)(ang->nu[2] - off_u * ang->dn[2]);
+    L.bu = (float)(nu_c - off_u * den_c);
+    L.av[0] = (float)(ang->nv[0] - off_v * ang->dn[0]);
+    L.av[1] = (float)(ang->nv[1] - off_v * ang->dn[1]);
+    L.av[2] = (float)(ang->nv[2] - off_v * ang->dn[2]);
+    L.bv = (float)(nv_c - off_v * den_c);
+    L.ad[0] = (float)ang->dn[0];
+    L.ad[1] = (float)ang->dn[1];
+    L.ad[2] = (float)ang->dn[2];
+    L.bd = (float)den_c;
+    L.u_lo = u_lo; L.v_lo = v_lo; L.wu = wu; L.wv = wv;
+    L.mode = mode;
+    L.weight = (float)ang->weight;
+    *out = L;
+}
+
+// Inner loop over the register-resident z run, sampling the staged footprint.
+template <bool CONE, bool CLAMP>
+__device__ __forceinline__ void bp_tile_loop(const float *__restrict__ b, float nu, float nv, float dn,
+                                             float su, float sv, float sd, float umax, float vmax,
+                                             float (&acc)[BP_ZPT])
+{
+    const float MAGIC = 12582912.0f;  // 1.5 * 2^23: floor() for 0 <= f < 2^22
+#pragma unroll
+    for (int i = 0; i < BP_ZPT; ++i) {
+        float fu, fv, w2;
+        if (CONE) {
+            const float r = __fdividef(1.0f, dn);
+            fu = nu * r; fv = nv * r; w2 = r * r;
+        } else {
+            fu = nu; fv = nv; w2 = 1.0f;
+        }
+        if (CLAMP) {  // NaN-safe: fmaxf/fminf return the non-NaN operand
+            fu = fminf(fmaxf(fu, 0.0f), umax);
+            fv = fminf(fmaxf(fv, 0.0f), vmax);
+        }
+        const float ru = (fu - 0.5f) + MAGIC, rv = (fv - 0.5f) + MAGIC;
+        const int iu = __float_as_int(ru) - 0x4B400000, iv = __float_as_int(rv) - 0x4B400000;
+        const float wu = fu - (ru - MAGIC), wv = fv - (rv - MAGIC);
+        const float *s = b + (iv * BP_PITCH + iu);
+        const float p00 = s[0], p10 = s[1], p01 = s[BP_PITCH], p11 = s[BP_PITCH + 1];
+        const float lo = fmaf(wu, p10 - p00, p00);
+        const float hi = fmaf(wu, p11 - p01, p01);
+        const float val = fmaf(wv, hi - lo, lo);
+        if (CONE) {
+            // behind-the-source voxels (w2 = inf) over an empty footprint must stay 0
+            acc[i] = CLAMP ? ((val != 0.0f) ? fmaf(w2, val, acc[i]) : acc[i]) : fmaf(w2, val, acc[i]);
+        } else {
+            acc[i] += val;
+        }
+        nu += su; nv += sv;
+        if (CONE) dn += sd;
+    }
+}
+
+template <bool CONE>
+__global__ void __launch_bounds__(BP_THREADS) bp_kernel(const BPArgs P)
+{
+    __shared__ float buf[BP_K][BP_WV * BP_PITCH];
+    __shared__ BPLocal loc[BP_K];
+
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int tid = ty * BP_TX + tx;
+    const int x0 = blockIdx.x * BP_TX, y0 = blockIdx.y * BP_TY, z0 = blockIdx.z * BP_ZPT;
+    const int x1 = min(x0 + BP_TX, P.nx) - 1, y1 = min(y0 + BP_TY, P.ny) - 1, z1 = min(z0 + BP_ZPT, P.nz) - 1;
+    // voxel-centre box of the tile in the normalised frame
+    const double xc = 0.5 * (x0 + x1) + 0.5 - 0.5 * P.nx, hx = 0.5 * (x1 - x0);
+    const double yc = 0.5 * (y0 + y1) + 0.5 - 0.5 * P.ny, hy = 0.5 * (y1 - y0);
+    const double zc = 0.5 * (z0 + z1) + 0.5 - 0.5 * P.nz, hz = 0.5 * (z1 - z0);
+
+    const int x = x0 + tx, y = y0 + ty;
+    const float dx = (float)((double)x + 0.5 - 0.5 * P.nx - xc);
+    const float dy = (float)((double)y + 0.5 - 0.5 * P.ny - yc);
+    const float dz0 = (float)((double)z0 + 0.5 - 0.5 * P.nz - zc);
+    const bool in_xy = (x < P.nx) && (y < P.ny);
+    const size_t row_pitch = (size_t)P.n_angles * P.det_u;
+
+    float acc[BP_ZPT];
+#pragma unroll
+    for (int i = 0; i < BP_ZPT; ++i) acc[i] = 0.0f;
+
+    for (int a0 = 0; a0 < P.n_angles; a0 += BP_K) {
+        const int na = min(BP_K, P.n_angles - a0);
+        __syncthreads();  // previous batch fully consumed
+        if (tid < 8 * BP_K) {
+            const int j = tid >> 3;
+            // clamp so that all 8 lanes of a group take part in the shuffles
+            const int a = a0 + min(j, na - 1);
+            bp_setup(P, P.angles + a, tid & 7, xc, yc, zc, hx, hy, hz, &loc[j]);
+        }
+        __syncthreads();
+        // stage footprints: warps over rows, lanes over columns
+        for (int j = 0; j < na; ++j) {
+            if (loc[j].mode != BP_SMEM && loc[j].mode != BP_SMEM_CLAMP) continue;
+            const int u_lo = loc[j].u_lo, v_lo = loc[j].v_lo, wu = loc[j].wu, wv = loc[j].wv;
+            const float w = CONE ? 1.0f : loc[j].weight;
+            const float *src = P.proj + (size_t)(a0 + j) * P.det_u;
+            for (int r = ty; r < wv; r += BP_TY) {
+                const int gv = v_lo + r;
+                const bool vin = (gv >= 0) && (gv < P.det_v);
+                for (int c = tx; c < wu; c += BP_TX) {
+                    const int gu = u_lo + c;
+                    float val = 0.0f;
+                    if (vin && gu >= 0 && gu < P.det_u) val = w * __ldg(src + (size_t)gv * row_pitch + gu);
+                    buf[j][r * BP_PITCH + c] = val;
+                }
+            }
+        }
+        __syncthreads();
+        if (!in_xy) continue;
+        for (int j = 0; j < na; ++j) {
+            const BPLocal &L = loc[j];
+            const int mode = L.mode;
+            if (mode == BP_SKIP) continue;
+            float nu = fmaf(L.au[0], dx, fmaf(L.au[1], dy, fmaf(L.au[2], dz0, L.bu)));
+            float nv = fmaf(L.av[0], dx, fmaf(L.av[1], dy, fmaf(L.av[2], dz0, L.bv)));
+            float dn = CONE ? fmaf(L.ad[0], dx, fmaf(L.ad[1], dy, fmaf(L.ad[2], dz0, L.bd))) : 1.0f;
+            const float su = L.au[2], sv = L.av[2], sd = L.ad[2];
+            if (mode == BP_SMEM) {
+                bp_tile_loop<CONE, false>(buf[j], nu, nv, dn, su, sv, sd, 0.0f, 0.0f, acc);
+            } else if (mode == BP_SMEM_CLAMP) {
+                bp_tile_loop<CONE, true>(buf[j], nu, nv, dn, su, sv, sd, (float)L.wu - 1.5f,
+                                         (float)L.wv - 1.5f, acc);
+            } else {
+                const float *src = P.proj + (size_t)(a0 + j) * P.det_u;
+                const float wpar = L.weight;
+#pragma unroll
+                for (int i = 0; i < BP_ZPT; ++i) {
+                    float fu, fv, w2;
+                    if (CONE) {
+                        const float r = 1.0f / dn;
+                        fu = nu * r; fv = nv * r; w2 = r * r;
+                    } else {
+                        fu = nu; fv = nv; w2 = wpar;
+                    }
+                    const float val = bp_sample_global(src, P.det_u, P.det_v, row_pitch, fu, fv);
+                    if (val != 0.0f) acc[i] = fmaf(w2, val, acc[i]);
+                    nu += su; nv += sv;
+                    if (CONE) dn += sd;
+                }
+            }
+        }
+    }
+    if (!in_xy) return;
+#pragma unroll
+    for (int i = 0; i < BP_ZPT; ++i) {
+        const int z = z0 + i;
+        if (z < P.nz) {
+            float *dst = P.vol + ((size_t)z * P.ny + y) * P.nx + x;
+            const float v = acc[i] * P.out_scale;
+            *dst = P.additive ? *dst + v : v;
+        }
+    }
+}
+
+// Voxel supersampling (rare, API parity with VoxelSuperSampling > 1): one
+// thread per voxel, direct bounds-checked gathers.
+template <bool CONE>
+__global__ void __launch_bounds__(256) bp_supersample_kernel(const BPArgs P)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    const int z = blockIdx.z;
+    if (x >= P.nx || y >= P.ny) return;
+    const int ss = P.vox_ss;
+    const size_t row_pitch = (size_t)P.n_angles * P.det_u;
+    float acc = 0.0f;
+    for (int a = 0; a < P.n_angles; ++a) {
+        const BPAngle *g = P.angles + a;
+        const float *src = P.proj + (size_t)a * P.det_u;
+        for (int sz = 0; sz < ss; ++sz)
+            for (int sy = 0; sy < ss; ++sy)
+                for (int sx = 0; sx < ss; ++sx) {
+                    const double px = x + (sx + 0.5) / ss - 0.5 * P.nx;
+                    const double py = y + (sy + 0.5) / ss - 0.5 * P.ny;
+                    const double pz = z + (sz + 0.5) / ss - 0.5 * P.nz;
+                    const double den = g->dn[0] * px + g->dn[1] * py + g->dn[2] * pz + g->dn[3];
+                    const double r = 1.0 / den;
+                    const float fu = (float)((g->nu[0] * px + g->nu[1] * py + g->nu[2] * pz + g->nu[3]) * r - 0.5);
+                    const float fv = (float)((g->nv[0] * px + g->nv[1] * py + g->nv[2] * pz + g->nv[3]) * r - 0.5);
+                    const float w = CONE ? (float)(r * r) : (float)g->weight;
+                    const float val = bp_sample_global(src, P.det_u, P.det_v, row_pitch, fu, fv);
+                    if (val != 0.0f) acc = fmaf(w, val, acc);
+                }
+    }
+    acc *= P.out_scale / (float)(ss * ss * ss);
+    float *dst = P.vol + ((size_t)z * P.ny + y) * P.nx + x;
+    *dst = P.additive ? *dst + acc : acc;
+}
+
+}  // namespace tsp

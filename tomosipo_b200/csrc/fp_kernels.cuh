@@ -1,0 +1,216 @@
+// Forward projection: ray-driven Joseph march with bilinear in-slice
+// interpolation (semantics: SURVEY.md B.1; call site tomosipo/astra.py:147-153).
+//
+// Mapping: one thread per detector pixel, lanes of a warp along det_u, one
+// angle per CTA.  All angles of a launch march along the same volume axis and
+// read a layout whose in-slice axis `p` is memory-contiguous, so that a warp's
+// four bilinear taps fall into one or two 128-byte lines per slice.  Angles
+// whose in-slice axes are (y, z) read an (x<->y)-transposed copy of the volume
+// made once per call by transpose_xy_kernel.
+//
+// Every output pixel is written exactly once: the thread walks *all* slices,
+// unlike ASTRA's N/4 launches that read-modify-write the projections.
+#pragma once
+#include "tsp_internal.h"
+
+namespace tsp {
+
+constexpr int FP_BU = 32;  // det_u pixels per CTA (= warp width)
+constexpr int FP_BV = 8;   // det_v pixels per CTA
+
+struct FPArgs {
+    const float *vol;     // volume in the layout of this group
+    long long stride_m;   // elements between consecutive slices
+    long long stride_q;   // elements between consecutive q rows (p stride is 1)
+    int n_m, n_p, n_q;
+    const FPAngle *angles;
+    const int *list;      // angle ids of this group
+    float *proj;
+    int det_u, det_v, n_angles;
+    int additive;
+    int det_ss;
+    float sigma_m;        // voxel size along the march axis
+    float rp2, rq2;       // (sigma_p / sigma_m)^2, (sigma_q / sigma_m)^2
+};
+
+__device__ __forceinline__ int warp_min_i(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = min(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ int warp_max_i(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// k-interval on which  lo < a * (k + t0) + c < hi.  Returns [k_first, k_last]
+// as floats (may be empty / infinite); the caller rounds and clamps.
+__device__ __forceinline__ void k_interval(float a, float c, float t0, float lo, float hi,
+                                           float &k_first, float &k_last)
+{
+    if (fabsf(a) < 1e-12f) {
+        const bool in = (c > lo) && (c < hi);
+        k_first = in ? -1e30f : 1e30f;
+        k_last = in ? 1e30f : -1e30f;
+        return;
+    }
+    const float inv = 1.0f / a;
+    float t1 = (lo - c) * inv, t2 = (hi - c) * inv;
+    if (t1 > t2) { const float s = t1; t1 = t2; t2 = s; }
+    k_first = t1 - t0;
+    k_last = t2 - t0;
+}
+
+__device__ __forceinline__ int clamp_f2i(float x, int lo, int hi, bool round_up)
+{
+    x = fminf(fmaxf(x, (float)lo - 1.0f), (float)hi + 1.0f);
+    const int i = round_up ? __float2int_ru(x) : __float2int_rd(x);
+    return min(max(i, lo), hi);
+}
+
+// Line integral of one ray through the whole volume.  `live` = false lanes
+// carry a harmless dummy ray so that warp-uniform loops stay in bounds.
+__device__ __forceinline__ float march_ray(const FPArgs &P, bool live, double dir_m, double dir_p,
+                                           double dir_q, double org_m, double org_p, double org_q)
+{
+    const double inv = 1.0 / dir_m;
+    const double a_p = dir_p * inv, a_q = dir_q * inv;
+    float ap = (float)a_p, aq = (float)a_q;
+    // index-space intercepts: f = a * t_k + c, voxel i centred on f == i
+    float cp = (float)(org_p - a_p * org_m + 0.5 * P.n_p - 0.5);
+    float cq = (float)(org_q - a_q * org_m + 0.5 * P.n_q - 0.5);
+    const float t0 = 0.5f - 0.5f * (float)P.n_m;
+    const float scale = P.sigma_m * sqrtf(1.0f + ap * ap * P.rp2 + aq * aq * P.rq2);
+
+    // slices on which the ray touches the volume, and on which all four taps
+    // are guaranteed in bounds
+    int k_lo = P.n_m, k_hi = 0, in_lo = 0, in_hi = P.n_m;
+    if (live) {
+        float f1, l1, f2, l2;
+        k_interval(ap, cp, t0, -1.0f, (float)P.n_p, f1, l1);
+        k_interval(aq, cq, t0, -1.0f, (float)P.n_q, f2, l2);
+        k_lo = clamp_f2i(fmaxf(f1, f2) - 1.0f, 0, P.n_m, false);
+        k_hi = clamp_f2i(fminf(l1, l2) + 1.0f, 0, P.n_m, true);  // exclusive
+        k_interval(ap, cp, t0, 1.0f, (float)P.n_p - 2.0f, f1, l1);
+        k_interval(aq, cq, t0, 1.0f, (float)P.n_q - 2.0f, f2, l2);
+        in_lo = clamp_f2i(fmaxf(f1, f2), 0, P.n_m, true);
+        in_hi = clamp_f2i(fminf(l1, l2), -1, P.n_m - 1, false) + 1;  // exclusive
+        if (P.n_p < 4 || P.n_q < 4 || in_hi <= in_lo) { in_lo = P.n_m; in_hi = 0; }
+        if (k_hi <= k_lo) live = false;
+    }
+    if (!live) {  // dummy: stays on an interior voxel for every slice
+        ap = 0.0f; aq = 0.0f; cp = 1.0f; cq = 1.0f;
+        k_lo = P.n_m; k_hi = 0; in_lo = 0; in_hi = P.n_m;
+    }
+    const int kA = warp_min_i(k_lo);
+    const int kD = warp_max_i(k_hi);
+    if (kD <= kA) return 0.0f;
+    int kB = max(warp_max_i(in_lo), kA);
+    int kC = min(warp_min_i(in_hi), kD);
+    if (kB >= kC) { kB = kD; kC = kD; }
+
+    float acc = 0.0f;
+    const float *__restrict__ vol = P.vol;
+    const long long sm = P.stride_m, sq = P.stride_q;
+
+    auto careful = [&](int k_begin, int k_end) {
+        for (int k = k_begin; k < k_end; ++k) {
+            const float t = (float)k + t0;
+            const float fp = fmaf(ap, t, cp), fq = fmaf(aq, t, cq);
+            const float flp = floorf(fp), flq = floorf(fq);
+            const int ip = (int)flp, iq = (int)flq;
+            const float wp = fp - flp, wq = fq - flq;
+            const bool p0 = (ip >= 0) && (ip < P.n_p), p1 = (ip >= -1) && (ip + 1 < P.n_p);
+            const bool q0 = (iq >= 0) && (iq < P.n_q), q1 = (iq >= -1) && (iq + 1 < P.n_q);
+            const float *s = vol + (long long)k * sm + (long long)iq * sq + ip;
+            const float v00 = (p0 && q0) ? __ldg(s) : 0.0f;
+            const float v10 = (p1 && q0) ? __ldg(s + 1) : 0.0f;
+            const float v01 = (p0 && q1) ? __ldg(s + sq) : 0.0f;
+            const float v11 = (p1 && q1) ? __ldg(s + sq + 1) : 0.0f;
+            const float lo = fmaf(wp, v10 - v00, v00);
+            const float hi = fmaf(wp, v11 - v01, v01);
+            acc += fmaf(wq, hi - lo, lo);
+        }
+    };
+
+    careful(kA, kB);
+    {
+        // Interior slices: no bounds checks; floor() by the 1.5*2^23 trick
+        // (valid for 0 <= f < 2^22; ties may round down with weight exactly 1,
+        // which interpolates to the same value).
+        const float MAGIC = 12582912.0f;
+        const int sq32 = (int)sq;
+        const float *slice = vol + (long long)kB * sm;
+#pragma unroll 4
+        for (int k = kB; k < kC; ++k) {
+            const float t = (float)k + t0;
+            const float fp = fmaf(ap, t, cp), fq = fmaf(aq, t, cq);
+            const float rp = (fp - 0.5f) + MAGIC, rq = (fq - 0.5f) + MAGIC;
+            const int ip = __float_as_int(rp) - 0x4B400000, iq = __float_as_int(rq) - 0x4B400000;
+            const float wp = fp - (rp - MAGIC), wq = fq - (rq - MAGIC);
+            const float *s = slice + (iq * sq32 + ip);
+            const float v00 = __ldg(s), v10 = __ldg(s + 1);
+            const float v01 = __ldg(s + sq32), v11 = __ldg(s + sq32 + 1);
+            const float lo = fmaf(wp, v10 - v00, v00);
+            const float hi = fmaf(wp, v11 - v01, v01);
+            acc += fmaf(wq, hi - lo, lo);
+            slice += sm;
+        }
+    }
+    careful(kC, kD);
+    return live ? acc * scale : 0.0f;
+}
+
+template <bool CONE, bool SUPERSAMPLE>
+__global__ void __launch_bounds__(FP_BU *FP_BV) fp_kernel(const FPArgs P)
+{
+    const int a = P.list[blockIdx.z];
+    const FPAngle g = P.angles[a];
+    const int iu = blockIdx.x * FP_BU + threadIdx.x;
+    const int iv = blockIdx.y * FP_BV + threadIdx.y;
+    const bool live = (iu < P.det_u) && (iv < P.det_v);
+    const int ss = SUPERSAMPLE ? P.det_ss : 1;
+
+    float sum = 0.0f;
+    for (int sv = 0; sv < ss; ++sv) {
+        for (int su = 0; su < ss; ++su) {
+            const double cu = (double)iu + ((double)su + 0.5) / (double)ss;
+            const double cv = (double)iv + ((double)sv + 0.5) / (double)ss;
+            const double pm = g.d0[0] + cu * g.u[0] + cv * g.v[0];
+            const double pp = g.d0[1] + cu * g.u[1] + cv * g.v[1];
+            const double pq = g.d0[2] + cu * g.u[2] + cv * g.v[2];
+            if (CONE)
+                sum += march_ray(P, live, pm - g.o[0], pp - g.o[1], pq - g.o[2], g.o[0], g.o[1], g.o[2]);
+            else
+                sum += march_ray(P, live, g.o[0], g.o[1], g.o[2], pm, pp, pq);
+        }
+    }
+    if (SUPERSAMPLE) sum /= (float)(ss * ss);
+    if (live) {
+        float *dst = P.proj + ((size_t)iv * P.n_angles + a) * P.det_u + iu;
+        *dst = P.additive ? *dst + sum : sum;
+    }
+}
+
+// out[z][x][y] = in[z][y][x]
+__global__ void __launch_bounds__(256) transpose_xy_kernel(const float *__restrict__ in,
+                                                            float *__restrict__ out, int nx, int ny)
+{
+    __shared__ float tile[32][33];
+    const size_t plane = (size_t)nx * ny * blockIdx.z;
+    const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int x = x0 + threadIdx.x, y = y0 + r;
+        if (x < nx && y < ny) tile[r][threadIdx.x] = in[plane + (size_t)y * nx + x];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += 8) {
+        const int y = y0 + threadIdx.x, x = x0 + r;
+        if (x < nx && y < ny) out[plane + (size_t)x * ny + y] = tile[threadIdx.x][r];
+    }
+}
+
+}  // namespace tsp

@@ -1,0 +1,68 @@
+// Internal structures shared by the host side and the kernels of libtsproj.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "tsproj.h"
+
+namespace tsp {
+
+// One projection angle in the *normalised* frame (unit voxels, volume centred
+// on the origin), with every 3-vector permuted to (march, p, q) order so a
+// kernel never indexes a vector with a runtime axis id.  fp64: per-ray set-up
+// is done in double precision, the march itself in fp32.
+struct FPAngle {
+    double o[3];   // cone: source position; parallel: ray direction
+    double d0[3];  // lower-left *corner* of detector pixel (0, 0)
+    double u[3];
+    double v[3];
+};
+
+// Voxel -> detector map of one angle (normalised frame, (x, y, z, 1) order):
+//   U = nu.X / dn.X,  V = nv.X / dn.X   (texel-centre convention: pixel i spans [i, i+1))
+// cone:     dn is scaled so that 1/dn.X^2 is the ray-density weight
+// parallel: dn = (0,0,0,1) and `weight` carries 1/|u x v|
+struct BPAngle {
+    double nu[4];
+    double nv[4];
+    double dn[4];
+    double weight;
+};
+
+// One FP launch group: all angles that march along the same axis and read
+// the same volume layout.
+struct FPGroup {
+    int march;           // 0 x, 1 y, 2 z  (volume axis marched)
+    int p_axis, q_axis;  // in-slice axes; p is the memory-contiguous one
+    bool transposed;     // reads the (z, x, y) copy instead of (z, y, x)
+    std::vector<int> angles;
+};
+
+struct DeviceState {
+    FPAngle *fp_angles = nullptr;  // [n_angles], permuted per angle
+    int *fp_lists = nullptr;       // concatenated group lists
+    BPAngle *bp_angles = nullptr;  // [n_angles]
+    std::vector<size_t> list_offset;
+};
+
+}  // namespace tsp
+
+struct tsp_projector {
+    tsp_geometry g;
+    std::vector<double> vectors;
+    double sigma[3];
+    std::vector<tsp::FPAngle> fp_angles;
+    std::vector<int> march_axis;
+    std::vector<tsp::FPGroup> groups;
+    std::vector<tsp::BPAngle> bp_angles;
+    std::map<int, tsp::DeviceState> dev;
+    std::mutex mu;
+    int64_t launches = 0;
+    int bp_uses_tma = 0;
+    int fp_uses_transpose = 0;
+};
