@@ -1,0 +1,191 @@
+"""Backend boundary: geometry conversion and direct projection.
+
+API mirror of the reference's ``tomosipo/astra.py`` -- the file whose ASTRA
+calls this package replaces:
+
+=============================================  ================================
+reference (ASTRA)                              here (libtsproj C ABI)
+=============================================  ================================
+``astra.create_projector('cuda3d', pg, vg)``   ``tsp_projector_create``
+``astra.experimental.direct_FPBP3D(...)``      ``tsp_project``
+``astra.data3d.GPULink(ptr, x, y, z, pitch)``  ``links.base.RawBuffer``
+=============================================  ================================
+
+``to_astra`` / ``from_astra`` still produce / accept ASTRA-format dicts, so
+geometries interoperate with code written against ASTRA.
+"""
+import numpy as np
+
+import tomosipo_b200 as ts
+from . import _backend, astra_compat
+
+
+# ------------------------------------------------------------ geometry dicts --
+def from_astra(astra_geom):
+    """Import a 3D ASTRA volume or projection geometry dict."""
+    if not isinstance(astra_geom, dict):
+        raise TypeError(
+            f"Currently, tomosipo only supports importing ASTRA geometries. "
+            f"Objects of type {type(astra_geom)} are not supported. "
+            f"Perhaps you meant to use `ts.to_astra'? "
+        )
+    if "GridSliceCount" in astra_geom:
+        return ts.geometry.volume.from_astra(astra_geom)
+    return ts.geometry.conversion.from_astra_projection_geometry(astra_geom)
+
+
+def to_astra(x):
+    """Convert a volume or projection geometry to its ASTRA dict."""
+    try:
+        return x.to_astra()
+    except AttributeError:
+        raise TypeError(
+            f"The object of type {type(x)} does not support conversion to ASTRA."
+            f"Perhaps you meant to use `ts.from_astra'? "
+        )
+
+
+# ------------------------------------------------------------------ projector --
+def _projection_vectors(astra_pg):
+    """(kind, vectors) of an ASTRA projection dict; circular dicts go through geom_2vec."""
+    kind = astra_pg["type"]
+    if kind in ("cone", "parallel3d"):
+        astra_pg = astra_compat.geom_2vec(astra_pg)
+        kind = astra_pg["type"]
+    if kind == "cone_vec":
+        return _backend.KIND_CONE_VEC, astra_pg["Vectors"]
+    if kind == "parallel3d_vec":
+        return _backend.KIND_PARALLEL_VEC, astra_pg["Vectors"]
+    raise ValueError(f"Projection geometry of type '{kind}' cannot be used to create a projector.")
+
+
+def create_astra_projector(volume_geometry, projection_geometry, *, voxel_supersampling=1,
+                           detector_supersampling=1):
+    """Create the backend projector for a (volume, projection) geometry pair.
+
+    Same inputs as the reference (``tomosipo/astra.py:80-98``): an axis-aligned
+    ``VolumeGeometry`` and any projection geometry; both are first converted to
+    their ASTRA dicts, so the C library sees exactly what ASTRA would.
+    Returns an opaque handle (:class:`tomosipo_b200._backend.Projector`).
+    """
+    vg, pg = volume_geometry, projection_geometry
+    assert isinstance(vg, ts.geometry.VolumeGeometry)
+    avg, apg = vg.to_astra(), pg.to_astra()
+    kind, vectors = _projection_vectors(apg)
+    opt = avg["option"]
+    window = tuple((opt[f"WindowMin{a}"], opt[f"WindowMax{a}"]) for a in "XYZ")
+    return _backend.Projector(
+        kind,
+        (avg["GridSliceCount"], avg["GridRowCount"], avg["GridColCount"]),
+        window,
+        (apg["DetectorRowCount"], apg["DetectorColCount"]),
+        vectors,
+        voxel_supersampling=voxel_supersampling,
+        detector_supersampling=detector_supersampling,
+    )
+
+
+def direct_project(projector, vol_link, proj_link, forward=None, additive=False):
+    """Forward- or back-project between two linked arrays, in place.
+
+    Mirrors ``tomosipo/astra.py:104-153``: ``forward`` must be given; incompatible
+    links (different devices) raise ``ValueError``; ``additive`` selects ASTRA's
+    MODE_ADD instead of MODE_SET.  CUDA arrays are processed asynchronously on
+    their current stream; host arrays synchronously (H2D, kernels, D2H).
+    """
+    if forward is None:
+        raise ValueError("project must be given a forward argument (True/False).")
+    if not ts.links.are_compatible(vol_link, proj_link):
+        raise ValueError(
+            "Cannot perform ASTRA projection on volume and projection data, because they are not compatible. "
+            "Usually, this indicates that the data are located on different computing devices. "
+        )
+    with vol_link.context():
+        vol, proj = vol_link.linked_data, proj_link.linked_data
+        if tuple(vol.shape) != tuple(projector.vol_shape) or tuple(proj.shape) != tuple(projector.proj_shape):
+            raise ValueError(
+                f"Projector expects volume {projector.vol_shape} and projections {projector.proj_shape}; "
+                f"got {tuple(vol.shape)} and {tuple(proj.shape)}."
+            )
+        if vol.kind != proj.kind:
+            raise ValueError("Cannot project between host and device memory.")
+        on_device = vol.kind == "device"
+        projector.project(
+            _backend.FP if forward else _backend.BP,
+            additive,
+            vol.ptr,
+            proj.ptr,
+            _backend.MEM_DEVICE if on_device else _backend.MEM_HOST,
+            device=vol.device if on_device else _default_device(),
+            stream=vol.stream if on_device else 0,
+        )
+
+
+def _default_device():
+    """Device used for host arrays: torch's current device when torch is loaded, else 0."""
+    import sys
+
+    torch = sys.modules.get("torch")
+    if torch is not None and torch.cuda.is_available():
+        return torch.cuda.current_device()
+    return 0
+
+
+def direct_fp(projector, vol_data, proj_data, additive=False):
+    """``proj (+)= A vol`` on linked arrays (``tomosipo/astra.py:156-184``)."""
+    return direct_project(projector, vol_data, proj_data, forward=True, additive=additive)
+
+
+def direct_bp(projector, vol_data, proj_data, additive=False):
+    """``vol (+)= A^T proj`` on linked arrays (``tomosipo/astra.py:187-215``)."""
+    return direct_project(projector, vol_data, proj_data, forward=False, additive=additive)
+
+
+# ------------------------------------------------- legacy Data-based interface --
+def _as_list(x):
+    return list(x) if isinstance(x, (list, tuple)) else [x]
+
+
+def project(*data, voxel_supersampling=1, detector_supersampling=1, forward=None, additive=False, projector=None):
+    """All-to-all projection between ``Data`` volumes and ``Data`` projections.
+
+    Legacy interface of the reference (``tomosipo/astra.py:221-290``, built on
+    ``astra.experimental.do_composite``): every volume is projected onto every
+    projection dataset (forward), or every projection dataset is back-projected
+    into every volume (backward); contributions accumulate.
+    """
+    if forward is None:
+        raise ValueError("project must be given a forward argument (True/False).")
+    vols = [d for d in data if d.is_volume()]
+    projs = [d for d in data if d.is_projection()]
+    if not vols or not projs:
+        raise ValueError("Expected at least one projection dataset and one volume dataset")
+    targets = projs if forward else vols
+    for i, t in enumerate(targets):
+        first = not additive
+        for s in (vols if forward else projs):
+            v, p = (s, t) if forward else (t, s)
+            op = ts.operator(v.geometry, p.geometry, voxel_supersampling=voxel_supersampling,
+                             detector_supersampling=detector_supersampling)
+            direct_project(op.astra_projector, v.link, p.link, forward=forward, additive=not first)
+            first = False
+
+
+def forward(*data, voxel_supersampling=1, detector_supersampling=1, projector=None):
+    """Legacy forward projection of ``Data`` objects (``tomosipo/astra.py:293-330``)."""
+    project(*data, voxel_supersampling=voxel_supersampling, detector_supersampling=detector_supersampling,
+            forward=True, projector=projector)
+
+
+def backward(*data, voxel_supersampling=1, detector_supersampling=1, projector=None):
+    """Legacy backprojection of ``Data`` objects (``tomosipo/astra.py:333-371``)."""
+    project(*data, voxel_supersampling=voxel_supersampling, detector_supersampling=detector_supersampling,
+            forward=False, projector=projector)
+
+
+def fdk(vol_data, proj_data, *, voxel_supersampling=1, detector_supersampling=1):
+    """FDK reconstruction (``tomosipo/astra.py:374-406``): not on the projection hot path.
+
+    Listed as a "next" row in SURVEY.md 8f (ramp filter + FDK-weighted BP); not built yet.
+    """
+    raise NotImplementedError("ts.astra.fdk is outside the projection hot path and is not implemented yet.")

@@ -167,10 +167,13 @@ __device__ __forceinline__ float march_ray(const FPArgs &P, bool live, double di
 template <bool CONE, bool SUPERSAMPLE>
 __global__ void __launch_bounds__(FP_BU *FP_BV) fp_kernel(const FPArgs P)
 {
-    const int a = P.list[blockIdx.z];
+    // Grid order (x fastest): det_u tile, angle, det_v tile.  CTAs that run
+    // together share one det_v tile across many angles, i.e. (for the common
+    // geometries) one thin slab of the volume, which then stays L2-resident.
+    const int a = P.list[blockIdx.y];
     const FPAngle g = P.angles[a];
     const int iu = blockIdx.x * FP_BU + threadIdx.x;
-    const int iv = blockIdx.y * FP_BV + threadIdx.y;
+    const int iv = blockIdx.z * FP_BV + threadIdx.y;
     const bool live = (iu < P.det_u) && (iv < P.det_v);
     const int ss = SUPERSAMPLE ? P.det_ss : 1;
 

@@ -322,12 +322,12 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
         P.rq2 = (float)(rq * rq);
         const bool cone = g.kind == TSP_KIND_CONE_VEC;
         const bool ss = g.detector_supersampling > 1;
-        // gridDim.z is limited to 65535: chunk the angle list
+        // gridDim.y is limited to 65535: chunk the angle list
         for (size_t off = 0; off < grp.angles.size(); off += 65535) {
             const int na = (int)std::min<size_t>(65535, grp.angles.size() - off);
             FPArgs Q = P;
             Q.list = P.list + off;
-            dim3 grid((g.det_cols + FP_BU - 1) / FP_BU, (g.det_rows + FP_BV - 1) / FP_BV, na);
+            dim3 grid((g.det_cols + FP_BU - 1) / FP_BU, na, (g.det_rows + FP_BV - 1) / FP_BV);
             dim3 block(FP_BU, FP_BV);
             if (cone && !ss) fp_kernel<true, false><<<grid, block, 0, stream>>>(Q);
             else if (cone && ss) fp_kernel<true, true><<<grid, block, 0, stream>>>(Q);

@@ -150,7 +150,9 @@ def rotate(*, pos, axis, angles=None, rad=None, deg=None, right_handed=True):
     if not right_handed:
         theta = -theta
 
-    # Rodrigues: R = cos I + (1 - cos) a a^T + sin [a]_x, with a, theta broadcast
+    # Rodrigues in the left-handed (z, y, x) frame: R = cos I + (1 - cos) a a^T - sin [a]_x
+    # (the transpose of the textbook right-handed matrix, as in the reference,
+    # transform.py:413-431, whose rows are stacked as columns)
     n = vc.broadcast_lengths(len(theta), len(axis))
     a = np.broadcast_to(axis[:, :3], (n, 3))
     c = np.broadcast_to(np.cos(theta), (n,))
@@ -163,7 +165,7 @@ def rotate(*, pos, axis, angles=None, rad=None, deg=None, right_handed=True):
     R[:, :3, :3] = (
         c[:, None, None] * np.eye(3)[None]
         + (1 - c)[:, None, None] * a[:, :, None] * a[:, None, :]
-        + s[:, None, None] * K
+        - s[:, None, None] * K
     )
     R[:, 3, 3] = 1.0
     T = translate(-pos)
