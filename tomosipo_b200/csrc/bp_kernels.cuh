@@ -1,7 +1,7 @@
 // Backprojection: voxel-driven, bilinear detector interpolation, ray-density
 // weight (semantics: SURVEY.md B.2; call site tomosipo/astra.py:147-153).
 //
-// A CTA owns a BP_TX x BP_TY x BP_ZPT voxel tile and loops over *all* angles,
+// A CTA owns a BP_TX x BP_TY x ZPT voxel tile and loops over *all* angles,
 // so each voxel is written exactly once (ASTRA: one launch per 32 angles, each
 // read-modify-writing the volume).  Per angle batch the detector footprint of
 // the tile is staged into shared memory (zero-filled outside the detector,
@@ -16,12 +16,16 @@ namespace tsp {
 
 constexpr int BP_TX = 32;   // voxels along x per CTA (= warp width)
 constexpr int BP_TY = 8;    // voxels along y per CTA
-constexpr int BP_ZPT = 8;   // z voxels per thread (registers)
 constexpr int BP_K = 8;     // angles staged per batch
 constexpr int BP_WU = 64;   // staged footprint: max columns
-constexpr int BP_WV = 22;   // staged footprint: max rows
 constexpr int BP_PITCH = BP_WU + 1;
 constexpr int BP_THREADS = BP_TX * BP_TY;
+// staged footprint: max rows, as a function of the z voxels per thread (ZPT)
+__host__ __device__ constexpr int bp_wv(int zpt) { return zpt + 14; }
+__host__ __device__ constexpr size_t bp_smem_bytes(int zpt)
+{
+    return (size_t)BP_K * bp_wv(zpt) * BP_PITCH * sizeof(float);
+}
 
 // BP_SMEM_CLAMP: the footprint was clipped to the detector (+4 pixel zero margin), so
 // buffer coordinates are clamped into the zero margin before sampling.
@@ -49,6 +53,8 @@ struct BPLocal {
     int u_lo, v_lo, wu, wv;
     int mode;
     float weight;
+    int z_invariant;  // column and magnification do not change along the z run
+    int pad;
 };
 
 __device__ __forceinline__ float bp_sample_global(const float *__restrict__ proj, int det_u, int det_v,
@@ -73,7 +79,7 @@ __device__ __forceinline__ float bp_sample_global(const float *__restrict__ proj
 // box; shuffles reduce the bounding box; lane 0 writes the local map.
 __device__ __forceinline__ void bp_setup(const BPArgs &P, const BPAngle *__restrict__ ang, int corner,
                                          double xc, double yc, double zc, double hx, double hy,
-                                         double hz, BPLocal *out)
+                                         double hz, int max_rows, BPLocal *out)
 {
     const double den_c = ang->dn[0] * xc + ang->dn[1] * yc + ang->dn[2] * zc + ang->dn[3];
     const double nu_c = ang->nu[0] * xc + ang->nu[1] * yc + ang->nu[2] * zc + ang->nu[3];
@@ -118,7 +124,7 @@ __device__ __forceinline__ void bp_setup(const BPArgs &P, const BPAngle *__restr
             v_lo = (int)floor(vmin - 0.5) - 1;
             wu = (int)floor(umax - 0.5) + 3 - u_lo;
             wv = (int)floor(vmax - 0.5) + 3 - v_lo;
-            if (wu > BP_WU || wv > BP_WV) {
+            if (wu > BP_WU || wv > max_rows) {
                 mode = BP_GLOBAL;
             } else {
                 off_u += (double)u_lo;
@@ -141,21 +147,45 @@ __device__ __forceinline__ void bp_setup(const BPArgs &P, const BPAngle *__restr
     L.u_lo = u_lo; L.v_lo = v_lo; L.wu = wu; L.wv = wv;
     L.mode = mode;
     L.weight = (float)ang->weight;
+    // U (and the cone magnification) independent of z over this tile?  Exact zeros for
+    // detectors whose rows are parallel to the z axis (all circular geometries).
+    const double au2 = ang->nu[2] - off_u * ang->dn[2];
+    L.z_invariant = ((fabs(au2) + 64.0 * fabs(ang->dn[2])) * (2.0 * hz + 1.0) < 1e-7 * fabs(den_c)) ? 1 : 0;
+    L.pad = 0;
     *out = L;
 }
 
-// Inner loop over the register-resident z run, sampling the staged footprint.
-template <bool CONE, bool CLAMP>
-__device__ __forceinline__ void bp_tile_loop(const float *__restrict__ b, float nu, float nv, float dn,
-                                             float su, float sv, float sd, float umax, float vmax,
-                                             float (&acc)[BP_ZPT])
+template <int OFF>
+__device__ __forceinline__ float lds_f32(uint32_t addr)
 {
-    const float MAGIC = 12582912.0f;  // 1.5 * 2^23: floor() for 0 <= f < 2^22
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+constexpr float BP_MAGIC = 12582912.0f;      // 1.5 * 2^23: a round-down add leaves floor(f) in the low mantissa bits (0 <= f < 2^22)
+constexpr uint32_t BP_MAGIC_BITS = 0x4B400000u;
+
+// Inner loop over the register-resident z run, sampling the staged footprint.
+// `sbase` is the shared-memory byte address of the footprint buffer.
+template <bool CONE, bool CLAMP, int ZPT>
+__device__ __forceinline__ void bp_tile_loop(uint32_t sbase, float nu, float nv, float dn, float su, float sv,
+                                             float sd, float umax, float vmax, float (&acc)[ZPT])
+{
+    // byte address = sbase + 4 * ((rv_bits - M) * PITCH + (ru_bits - M))
+    const uint32_t cbase = sbase - 4u * BP_MAGIC_BITS * (uint32_t)(BP_PITCH + 1);
 #pragma unroll
-    for (int i = 0; i < BP_ZPT; ++i) {
+    for (int i = 0; i < ZPT; ++i) {
         float fu, fv, w2;
         if (CONE) {
-            const float r = __fdividef(1.0f, dn);
+            const float r = rcp_approx(dn);
             fu = nu * r; fv = nv * r; w2 = r * r;
         } else {
             fu = nu; fv = nv; w2 = 1.0f;
@@ -164,11 +194,11 @@ __device__ __forceinline__ void bp_tile_loop(const float *__restrict__ b, float 
             fu = fminf(fmaxf(fu, 0.0f), umax);
             fv = fminf(fmaxf(fv, 0.0f), vmax);
         }
-        const float ru = (fu - 0.5f) + MAGIC, rv = (fv - 0.5f) + MAGIC;
-        const int iu = __float_as_int(ru) - 0x4B400000, iv = __float_as_int(rv) - 0x4B400000;
-        const float wu = fu - (ru - MAGIC), wv = fv - (rv - MAGIC);
-        const float *s = b + (iv * BP_PITCH + iu);
-        const float p00 = s[0], p10 = s[1], p01 = s[BP_PITCH], p11 = s[BP_PITCH + 1];
+        const float ru = __fadd_rd(fu, BP_MAGIC), rv = __fadd_rd(fv, BP_MAGIC);  // round-down add == floor
+        const float wu = fu - (ru - BP_MAGIC), wv = fv - (rv - BP_MAGIC);
+        const uint32_t a = (__float_as_uint(rv) * (uint32_t)BP_PITCH + __float_as_uint(ru)) * 4u + cbase;
+        const float p00 = lds_f32<0>(a), p10 = lds_f32<4>(a);
+        const float p01 = lds_f32<4 * BP_PITCH>(a), p11 = lds_f32<4 * BP_PITCH + 4>(a);
         const float lo = fmaf(wu, p10 - p00, p00);
         const float hi = fmaf(wu, p11 - p01, p01);
         const float val = fmaf(wv, hi - lo, lo);
@@ -183,10 +213,42 @@ __device__ __forceinline__ void bp_tile_loop(const float *__restrict__ b, float 
     }
 }
 
-template <bool CONE>
+// Same, for angles whose detector column and magnification are constant along
+// z (detector rows parallel to the z axis): the column, its weight and the
+// ray-density weight are computed once per (x, y); only the row moves.
+template <bool CONE, int ZPT>
+__device__ __forceinline__ void bp_tile_loop_zinv(uint32_t sbase, float nu, float nv, float dn, float sv,
+                                                  float (&acc)[ZPT])
+{
+    float r = 1.0f, w2 = 1.0f;
+    if (CONE) { r = rcp_approx(dn); w2 = r * r; }
+    const float fu = nu * r;
+    const float ru = __fadd_rd(fu, BP_MAGIC);
+    const float wu = fu - (ru - BP_MAGIC);
+    const uint32_t cbase = sbase - 4u * BP_MAGIC_BITS * (uint32_t)(BP_PITCH + 1) + 4u * __float_as_uint(ru);
+    float fv = nv * r;
+    const float dv = sv * r;
+#pragma unroll
+    for (int i = 0; i < ZPT; ++i) {
+        const float rv = __fadd_rd(fv, BP_MAGIC);
+        const float wv = fv - (rv - BP_MAGIC);
+        const uint32_t a = __float_as_uint(rv) * (uint32_t)(4 * BP_PITCH) + cbase;
+        const float p00 = lds_f32<0>(a), p10 = lds_f32<4>(a);
+        const float p01 = lds_f32<4 * BP_PITCH>(a), p11 = lds_f32<4 * BP_PITCH + 4>(a);
+        const float lo = fmaf(wu, p10 - p00, p00);
+        const float hi = fmaf(wu, p11 - p01, p01);
+        const float val = fmaf(wv, hi - lo, lo);
+        acc[i] = CONE ? fmaf(w2, val, acc[i]) : acc[i] + val;
+        fv += dv;
+    }
+}
+
+template <bool CONE, int BP_ZPT>
 __global__ void __launch_bounds__(BP_THREADS) bp_kernel(const BPArgs P)
 {
-    __shared__ float buf[BP_K][BP_WV * BP_PITCH];
+    constexpr int BP_WV = bp_wv(BP_ZPT);
+    extern __shared__ __align__(16) float bp_dyn_smem[];
+    float(*buf)[BP_WV * BP_PITCH] = reinterpret_cast<float(*)[BP_WV * BP_PITCH]>(bp_dyn_smem);
     __shared__ BPLocal loc[BP_K];
 
     const int tx = threadIdx.x, ty = threadIdx.y;
@@ -216,7 +278,7 @@ __global__ void __launch_bounds__(BP_THREADS) bp_kernel(const BPArgs P)
             const int j = tid >> 3;
             // clamp so that all 8 lanes of a group take part in the shuffles
             const int a = a0 + min(j, na - 1);
-            bp_setup(P, P.angles + a, tid & 7, xc, yc, zc, hx, hy, hz, &loc[j]);
+            bp_setup(P, P.angles + a, tid & 7, xc, yc, zc, hx, hy, hz, BP_WV, &loc[j]);
         }
         __syncthreads();
         // stage footprints: warps over rows, lanes over columns
@@ -246,11 +308,13 @@ __global__ void __launch_bounds__(BP_THREADS) bp_kernel(const BPArgs P)
             float nv = fmaf(L.av[0], dx, fmaf(L.av[1], dy, fmaf(L.av[2], dz0, L.bv)));
             float dn = CONE ? fmaf(L.ad[0], dx, fmaf(L.ad[1], dy, fmaf(L.ad[2], dz0, L.bd))) : 1.0f;
             const float su = L.au[2], sv = L.av[2], sd = L.ad[2];
+            const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(buf[j]);
             if (mode == BP_SMEM) {
-                bp_tile_loop<CONE, false>(buf[j], nu, nv, dn, su, sv, sd, 0.0f, 0.0f, acc);
+                if (L.z_invariant) bp_tile_loop_zinv<CONE, BP_ZPT>(sbase, nu, nv, dn, sv, acc);
+                else bp_tile_loop<CONE, false, BP_ZPT>(sbase, nu, nv, dn, su, sv, sd, 0.0f, 0.0f, acc);
             } else if (mode == BP_SMEM_CLAMP) {
-                bp_tile_loop<CONE, true>(buf[j], nu, nv, dn, su, sv, sd, (float)L.wu - 1.5f,
-                                         (float)L.wv - 1.5f, acc);
+                bp_tile_loop<CONE, true, BP_ZPT>(sbase, nu, nv, dn, su, sv, sd, (float)L.wu - 1.5f,
+                                                 (float)L.wv - 1.5f, acc);
             } else {
                 const float *src = P.proj + (size_t)(a0 + j) * P.det_u;
                 const float wpar = L.weight;

@@ -31,6 +31,7 @@ struct FPArgs {
     int det_ss;
     float sigma_m;        // voxel size along the march axis
     float rp2, rq2;       // (sigma_p / sigma_m)^2, (sigma_q / sigma_m)^2
+    int offsets_fit_32bit;  // volume has < 2^31 elements: the interior loop may use 32-bit offsets
 };
 
 __device__ __forceinline__ int warp_min_i(int v)
@@ -98,7 +99,7 @@ __device__ __forceinline__ float march_ray(const FPArgs &P, bool live, double di
         k_interval(aq, cq, t0, 1.0f, (float)P.n_q - 2.0f, f2, l2);
         in_lo = clamp_f2i(fmaxf(f1, f2), 0, P.n_m, true);
         in_hi = clamp_f2i(fminf(l1, l2), -1, P.n_m - 1, false) + 1;  // exclusive
-        if (P.n_p < 4 || P.n_q < 4 || in_hi <= in_lo) { in_lo = P.n_m; in_hi = 0; }
+        if (P.n_p < 4 || P.n_q < 4 || in_hi <= in_lo || !P.offsets_fit_32bit) { in_lo = P.n_m; in_hi = 0; }
         if (k_hi <= k_lo) live = false;
     }
     if (!live) {  // dummy: stays on an interior voxel for every slice
@@ -138,26 +139,30 @@ __device__ __forceinline__ float march_ray(const FPArgs &P, bool live, double di
 
     careful(kA, kB);
     {
-        // Interior slices: no bounds checks; floor() by the 1.5*2^23 trick
-        // (valid for 0 <= f < 2^22; ties may round down with weight exactly 1,
-        // which interpolates to the same value).
+        // Interior slices: no bounds checks; floor() by adding 1.5*2^23 with
+        // round-down (valid for 0 <= f < 2^22): the sum's low mantissa bits are
+        // floor(f).  Element offsets are 32-bit:
+        // off = k*sm + iq*sq + ip, with the magic-number bias folded into koff.
         const float MAGIC = 12582912.0f;
-        const int sq32 = (int)sq;
-        const float *slice = vol + (long long)kB * sm;
+        const uint32_t MBITS = 0x4B400000u;
+        const uint32_t sq32 = (uint32_t)sq, sm32 = (uint32_t)sm;
+        uint32_t koff = (uint32_t)kB * sm32 - MBITS * (sq32 + 1u);
+        float t = (float)kB + t0;
 #pragma unroll 4
         for (int k = kB; k < kC; ++k) {
-            const float t = (float)k + t0;
             const float fp = fmaf(ap, t, cp), fq = fmaf(aq, t, cq);
-            const float rp = (fp - 0.5f) + MAGIC, rq = (fq - 0.5f) + MAGIC;
-            const int ip = __float_as_int(rp) - 0x4B400000, iq = __float_as_int(rq) - 0x4B400000;
+            const float rp = __fadd_rd(fp, MAGIC), rq = __fadd_rd(fq, MAGIC);  // round-down add == floor
             const float wp = fp - (rp - MAGIC), wq = fq - (rq - MAGIC);
-            const float *s = slice + (iq * sq32 + ip);
-            const float v00 = __ldg(s), v10 = __ldg(s + 1);
-            const float v01 = __ldg(s + sq32), v11 = __ldg(s + sq32 + 1);
+            const uint32_t off = __float_as_uint(rq) * sq32 + __float_as_uint(rp) + koff;
+            const float *s0 = vol + off;
+            const float *s1 = vol + (off + sq32);
+            const float v00 = __ldg(s0), v10 = __ldg(s0 + 1);
+            const float v01 = __ldg(s1), v11 = __ldg(s1 + 1);
             const float lo = fmaf(wp, v10 - v00, v00);
             const float hi = fmaf(wp, v11 - v01, v01);
             acc += fmaf(wq, hi - lo, lo);
-            slice += sm;
+            t += 1.0f;
+            koff += sm32;
         }
     }
     careful(kC, kD);

@@ -9,6 +9,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "bp_kernels.cuh"
@@ -320,6 +321,7 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
         const double rq = pr->sigma[grp.q_axis] / pr->sigma[grp.march];
         P.rp2 = (float)(rp * rp);
         P.rq2 = (float)(rq * rq);
+        P.offsets_fit_32bit = nvox < (1ull << 31) ? 1 : 0;
         const bool cone = g.kind == TSP_KIND_CONE_VEC;
         const bool ss = g.detector_supersampling > 1;
         // gridDim.y is limited to 65535: chunk the angle list
@@ -341,6 +343,51 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
     return TSP_OK;
 }
 
+// z voxels per thread: long register runs amortise per-angle set-up and footprint staging;
+// thin volumes (slabs, cfg 5) use short runs.  TSP_BP_ZPT overrides (tuning aid).
+static int bp_zpt_choice(int nz)
+{
+    if (const char *e = getenv("TSP_BP_ZPT")) {
+        const int v = atoi(e);
+        if (v == 1 || v == 4 || v == 8 || v == 16) return v;
+    }
+    if (nz >= 12) return 16;
+    if (nz > 4) return 8;
+    if (nz > 1) return 4;
+    return 1;
+}
+
+template <bool CONE, int ZPT>
+static int launch_bp_one(dim3 grid, dim3 block, cudaStream_t stream, const BPArgs &P)
+{
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t smem = bp_smem_bytes(ZPT);
+    if (dev < 64 && !configured[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(bp_kernel<CONE, ZPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev] = true;
+    }
+    bp_kernel<CONE, ZPT><<<grid, block, smem, stream>>>(P);
+    return TSP_OK;
+}
+
+static int launch_bp_variant(bool cone, int zpt, dim3 grid, dim3 block, cudaStream_t stream, const BPArgs &P)
+{
+#define TSP_BP_CASE(Z)                                                          \
+    case Z:                                                                     \
+        return cone ? launch_bp_one<true, Z>(grid, block, stream, P)            \
+                    : launch_bp_one<false, Z>(grid, block, stream, P);
+    switch (zpt) {
+        TSP_BP_CASE(1)
+        TSP_BP_CASE(4)
+        TSP_BP_CASE(8)
+        TSP_BP_CASE(16)
+    }
+#undef TSP_BP_CASE
+    return fail(TSP_ERR_INVALID, "unsupported z run %d", zpt);
+}
+
 static int launch_bp(tsp_projector *pr, DeviceState *st, float *vol, const float *proj, int additive,
                      cudaStream_t stream)
 {
@@ -360,12 +407,12 @@ static int launch_bp(tsp_projector *pr, DeviceState *st, float *vol, const float
         if (cone) bp_supersample_kernel<true><<<grid, block, 0, stream>>>(P);
         else bp_supersample_kernel<false><<<grid, block, 0, stream>>>(P);
     } else {
-        const int gz = (g.nz + BP_ZPT - 1) / BP_ZPT;
+        const int zpt = bp_zpt_choice(g.nz);
+        const int gz = (g.nz + zpt - 1) / zpt;
         const int gy = (g.ny + BP_TY - 1) / BP_TY;
         if (gz > 65535 || gy > 65535) return fail(TSP_ERR_INVALID, "volume too large for the BP grid");
         dim3 grid((g.nx + BP_TX - 1) / BP_TX, gy, gz), block(BP_TX, BP_TY);
-        if (cone) bp_kernel<true><<<grid, block, 0, stream>>>(P);
-        else bp_kernel<false><<<grid, block, 0, stream>>>(P);
+        if (int rc = launch_bp_variant(cone, zpt, grid, block, stream, P)) return rc;
     }
     ++pr->launches;
     pr->bp_uses_tma = 0;
