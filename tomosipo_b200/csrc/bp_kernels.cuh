@@ -79,7 +79,7 @@ __device__ __forceinline__ float bp_sample_global(const float *__restrict__ proj
 // box; shuffles reduce the bounding box; lane 0 writes the local map.
 __device__ __forceinline__ void bp_setup(const BPArgs &P, const BPAngle *__restrict__ ang, int corner,
                                          double xc, double yc, double zc, double hx, double hy,
-                                         double hz, int max_rows, BPLocal *out)
+                                         double hz, int max_rows, int u_align, BPLocal *out)
 {
     const double den_c = ang->dn[0] * xc + ang->dn[1] * yc + ang->dn[2] * zc + ang->dn[3];
     const double nu_c = ang->nu[0] * xc + ang->nu[1] * yc + ang->nu[2] * zc + ang->nu[3];
@@ -121,6 +121,9 @@ __device__ __forceinline__ void bp_setup(const BPArgs &P, const BPAngle *__restr
             mode = BP_SKIP;  // footprint entirely off the detector
         } else {
             u_lo = (int)floor(umin - 0.5) - 1;
+            // TMA needs the innermost box coordinate on a 16-byte boundary (measured: any
+            // other start faults with "illegal instruction"); u_align = 4 floats there.
+            u_lo -= ((u_lo % u_align) + u_align) % u_align;
             v_lo = (int)floor(vmin - 0.5) - 1;
             wu = (int)floor(umax - 0.5) + 3 - u_lo;
             wv = (int)floor(vmax - 0.5) + 3 - v_lo;
@@ -175,12 +178,12 @@ constexpr uint32_t BP_MAGIC_BITS = 0x4B400000u;
 
 // Inner loop over the register-resident z run, sampling the staged footprint.
 // `sbase` is the shared-memory byte address of the footprint buffer.
-template <bool CONE, bool CLAMP, int ZPT>
+template <bool CONE, bool CLAMP, int ZPT, int PITCH>
 __device__ __forceinline__ void bp_tile_loop(uint32_t sbase, float nu, float nv, float dn, float su, float sv,
-                                             float sd, float umax, float vmax, float (&acc)[ZPT])
+                                             float sd, float umax, float vmax, float wpar, float (&acc)[ZPT])
 {
     // byte address = sbase + 4 * ((rv_bits - M) * PITCH + (ru_bits - M))
-    const uint32_t cbase = sbase - 4u * BP_MAGIC_BITS * (uint32_t)(BP_PITCH + 1);
+    const uint32_t cbase = sbase - 4u * BP_MAGIC_BITS * (uint32_t)(PITCH + 1);
 #pragma unroll
     for (int i = 0; i < ZPT; ++i) {
         float fu, fv, w2;
@@ -188,7 +191,7 @@ __device__ __forceinline__ void bp_tile_loop(uint32_t sbase, float nu, float nv,
             const float r = rcp_approx(dn);
             fu = nu * r; fv = nv * r; w2 = r * r;
         } else {
-            fu = nu; fv = nv; w2 = 1.0f;
+            fu = nu; fv = nv; w2 = wpar;
         }
         if (CLAMP) {  // NaN-safe: fmaxf/fminf return the non-NaN operand
             fu = fminf(fmaxf(fu, 0.0f), umax);
@@ -196,18 +199,14 @@ __device__ __forceinline__ void bp_tile_loop(uint32_t sbase, float nu, float nv,
         }
         const float ru = __fadd_rd(fu, BP_MAGIC), rv = __fadd_rd(fv, BP_MAGIC);  // round-down add == floor
         const float wu = fu - (ru - BP_MAGIC), wv = fv - (rv - BP_MAGIC);
-        const uint32_t a = (__float_as_uint(rv) * (uint32_t)BP_PITCH + __float_as_uint(ru)) * 4u + cbase;
+        const uint32_t a = (__float_as_uint(rv) * (uint32_t)PITCH + __float_as_uint(ru)) * 4u + cbase;
         const float p00 = lds_f32<0>(a), p10 = lds_f32<4>(a);
-        const float p01 = lds_f32<4 * BP_PITCH>(a), p11 = lds_f32<4 * BP_PITCH + 4>(a);
+        const float p01 = lds_f32<4 * PITCH>(a), p11 = lds_f32<4 * PITCH + 4>(a);
         const float lo = fmaf(wu, p10 - p00, p00);
         const float hi = fmaf(wu, p11 - p01, p01);
         const float val = fmaf(wv, hi - lo, lo);
-        if (CONE) {
-            // behind-the-source voxels (w2 = inf) over an empty footprint must stay 0
-            acc[i] = CLAMP ? ((val != 0.0f) ? fmaf(w2, val, acc[i]) : acc[i]) : fmaf(w2, val, acc[i]);
-        } else {
-            acc[i] += val;
-        }
+        // behind-the-source voxels (w2 = inf) over an empty footprint must stay 0
+        acc[i] = (CONE && CLAMP) ? ((val != 0.0f) ? fmaf(w2, val, acc[i]) : acc[i]) : fmaf(w2, val, acc[i]);
         nu += su; nv += sv;
         if (CONE) dn += sd;
     }
@@ -216,30 +215,83 @@ __device__ __forceinline__ void bp_tile_loop(uint32_t sbase, float nu, float nv,
 // Same, for angles whose detector column and magnification are constant along
 // z (detector rows parallel to the z axis): the column, its weight and the
 // ray-density weight are computed once per (x, y); only the row moves.
-template <bool CONE, int ZPT>
+template <bool CONE, int ZPT, int PITCH>
 __device__ __forceinline__ void bp_tile_loop_zinv(uint32_t sbase, float nu, float nv, float dn, float sv,
-                                                  float (&acc)[ZPT])
+                                                  float wpar, float (&acc)[ZPT])
 {
-    float r = 1.0f, w2 = 1.0f;
+    float r = 1.0f, w2 = wpar;
     if (CONE) { r = rcp_approx(dn); w2 = r * r; }
     const float fu = nu * r;
     const float ru = __fadd_rd(fu, BP_MAGIC);
     const float wu = fu - (ru - BP_MAGIC);
-    const uint32_t cbase = sbase - 4u * BP_MAGIC_BITS * (uint32_t)(BP_PITCH + 1) + 4u * __float_as_uint(ru);
+    const uint32_t cbase = sbase - 4u * BP_MAGIC_BITS * (uint32_t)(PITCH + 1) + 4u * __float_as_uint(ru);
     float fv = nv * r;
     const float dv = sv * r;
 #pragma unroll
     for (int i = 0; i < ZPT; ++i) {
         const float rv = __fadd_rd(fv, BP_MAGIC);
         const float wv = fv - (rv - BP_MAGIC);
-        const uint32_t a = __float_as_uint(rv) * (uint32_t)(4 * BP_PITCH) + cbase;
+        const uint32_t a = __float_as_uint(rv) * (uint32_t)(4 * PITCH) + cbase;
         const float p00 = lds_f32<0>(a), p10 = lds_f32<4>(a);
-        const float p01 = lds_f32<4 * BP_PITCH>(a), p11 = lds_f32<4 * BP_PITCH + 4>(a);
+        const float p01 = lds_f32<4 * PITCH>(a), p11 = lds_f32<4 * PITCH + 4>(a);
         const float lo = fmaf(wu, p10 - p00, p00);
         const float hi = fmaf(wu, p11 - p01, p01);
         const float val = fmaf(wv, hi - lo, lo);
-        acc[i] = CONE ? fmaf(w2, val, acc[i]) : acc[i] + val;
+        acc[i] = fmaf(w2, val, acc[i]);
         fv += dv;
+    }
+}
+
+// One angle's contribution to a thread's z run.  `L` lives in shared memory;
+// `sbase` is the shared byte address of the staged footprint (row pitch PITCH).
+template <bool CONE, int ZPT, int PITCH>
+__device__ __forceinline__ void bp_accumulate_angle(const BPArgs &P, const BPLocal &L, uint32_t sbase, int angle,
+                                                    float dx, float dy, float dz0, size_t row_pitch,
+                                                    float (&acc)[ZPT])
+{
+    const int mode = L.mode;
+    if (mode == BP_SKIP) return;
+    float nu = fmaf(L.au[0], dx, fmaf(L.au[1], dy, fmaf(L.au[2], dz0, L.bu)));
+    float nv = fmaf(L.av[0], dx, fmaf(L.av[1], dy, fmaf(L.av[2], dz0, L.bv)));
+    float dn = CONE ? fmaf(L.ad[0], dx, fmaf(L.ad[1], dy, fmaf(L.ad[2], dz0, L.bd))) : 1.0f;
+    const float su = L.au[2], sv = L.av[2], sd = L.ad[2];
+    const float wpar = L.weight;
+    if (mode == BP_SMEM) {
+        if (L.z_invariant) bp_tile_loop_zinv<CONE, ZPT, PITCH>(sbase, nu, nv, dn, sv, wpar, acc);
+        else bp_tile_loop<CONE, false, ZPT, PITCH>(sbase, nu, nv, dn, su, sv, sd, 0.0f, 0.0f, wpar, acc);
+    } else if (mode == BP_SMEM_CLAMP) {
+        bp_tile_loop<CONE, true, ZPT, PITCH>(sbase, nu, nv, dn, su, sv, sd, (float)L.wu - 1.5f, (float)L.wv - 1.5f,
+                                             wpar, acc);
+    } else {
+        const float *src = P.proj + (size_t)angle * P.det_u;
+#pragma unroll
+        for (int i = 0; i < ZPT; ++i) {
+            float fu, fv, w2;
+            if (CONE) {
+                const float r = 1.0f / dn;
+                fu = nu * r; fv = nv * r; w2 = r * r;
+            } else {
+                fu = nu; fv = nv; w2 = wpar;
+            }
+            const float val = bp_sample_global(src, P.det_u, P.det_v, row_pitch, fu, fv);
+            if (val != 0.0f) acc[i] = fmaf(w2, val, acc[i]);
+            nu += su; nv += sv;
+            if (CONE) dn += sd;
+        }
+    }
+}
+
+template <int ZPT>
+__device__ __forceinline__ void bp_store(const BPArgs &P, int x, int y, int z0, const float (&acc)[ZPT])
+{
+#pragma unroll
+    for (int i = 0; i < ZPT; ++i) {
+        const int z = z0 + i;
+        if (z < P.nz) {
+            float *dst = P.vol + ((size_t)z * P.ny + y) * P.nx + x;
+            const float v = acc[i] * P.out_scale;
+            *dst = P.additive ? *dst + v : v;
+        }
     }
 }
 
@@ -254,7 +306,8 @@ __global__ void __launch_bounds__(BP_THREADS) bp_kernel(const BPArgs P)
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int tid = ty * BP_TX + tx;
     const int x0 = blockIdx.x * BP_TX, y0 = blockIdx.y * BP_TY, z0 = blockIdx.z * BP_ZPT;
-    const int x1 = min(x0 + BP_TX, P.nx) - 1, y1 = min(y0 + BP_TY, P.ny) - 1, z1 = min(z0 + BP_ZPT, P.nz) - 1;
+    // z is not clipped to the volume: every thread walks its whole z run (only the store is guarded)
+    const int x1 = min(x0 + BP_TX, P.nx) - 1, y1 = min(y0 + BP_TY, P.ny) - 1, z1 = z0 + BP_ZPT - 1;
     // voxel-centre box of the tile in the normalised frame
     const double xc = 0.5 * (x0 + x1) + 0.5 - 0.5 * P.nx, hx = 0.5 * (x1 - x0);
     const double yc = 0.5 * (y0 + y1) + 0.5 - 0.5 * P.ny, hy = 0.5 * (y1 - y0);
@@ -278,14 +331,13 @@ __global__ void __launch_bounds__(BP_THREADS) bp_kernel(const BPArgs P)
             const int j = tid >> 3;
             // clamp so that all 8 lanes of a group take part in the shuffles
             const int a = a0 + min(j, na - 1);
-            bp_setup(P, P.angles + a, tid & 7, xc, yc, zc, hx, hy, hz, BP_WV, &loc[j]);
+            bp_setup(P, P.angles + a, tid & 7, xc, yc, zc, hx, hy, hz, BP_WV, 1, &loc[j]);
         }
         __syncthreads();
         // stage footprints: warps over rows, lanes over columns
         for (int j = 0; j < na; ++j) {
             if (loc[j].mode != BP_SMEM && loc[j].mode != BP_SMEM_CLAMP) continue;
             const int u_lo = loc[j].u_lo, v_lo = loc[j].v_lo, wu = loc[j].wu, wv = loc[j].wv;
-            const float w = CONE ? 1.0f : loc[j].weight;
             const float *src = P.proj + (size_t)(a0 + j) * P.det_u;
             for (int r = ty; r < wv; r += BP_TY) {
                 const int gv = v_lo + r;
@@ -293,7 +345,7 @@ __global__ void __launch_bounds__(BP_THREADS) bp_kernel(const BPArgs P)
                 for (int c = tx; c < wu; c += BP_TX) {
                     const int gu = u_lo + c;
                     float val = 0.0f;
-                    if (vin && gu >= 0 && gu < P.det_u) val = w * __ldg(src + (size_t)gv * row_pitch + gu);
+                    if (vin && gu >= 0 && gu < P.det_u) val = __ldg(src + (size_t)gv * row_pitch + gu);
                     buf[j][r * BP_PITCH + c] = val;
                 }
             }
@@ -301,50 +353,159 @@ __global__ void __launch_bounds__(BP_THREADS) bp_kernel(const BPArgs P)
         __syncthreads();
         if (!in_xy) continue;
         for (int j = 0; j < na; ++j) {
-            const BPLocal &L = loc[j];
-            const int mode = L.mode;
-            if (mode == BP_SKIP) continue;
-            float nu = fmaf(L.au[0], dx, fmaf(L.au[1], dy, fmaf(L.au[2], dz0, L.bu)));
-            float nv = fmaf(L.av[0], dx, fmaf(L.av[1], dy, fmaf(L.av[2], dz0, L.bv)));
-            float dn = CONE ? fmaf(L.ad[0], dx, fmaf(L.ad[1], dy, fmaf(L.ad[2], dz0, L.bd))) : 1.0f;
-            const float su = L.au[2], sv = L.av[2], sd = L.ad[2];
-            const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(buf[j]);
-            if (mode == BP_SMEM) {
-                if (L.z_invariant) bp_tile_loop_zinv<CONE, BP_ZPT>(sbase, nu, nv, dn, sv, acc);
-                else bp_tile_loop<CONE, false, BP_ZPT>(sbase, nu, nv, dn, su, sv, sd, 0.0f, 0.0f, acc);
-            } else if (mode == BP_SMEM_CLAMP) {
-                bp_tile_loop<CONE, true, BP_ZPT>(sbase, nu, nv, dn, su, sv, sd, (float)L.wu - 1.5f,
-                                                 (float)L.wv - 1.5f, acc);
-            } else {
-                const float *src = P.proj + (size_t)(a0 + j) * P.det_u;
-                const float wpar = L.weight;
-#pragma unroll
-                for (int i = 0; i < BP_ZPT; ++i) {
-                    float fu, fv, w2;
-                    if (CONE) {
-                        const float r = 1.0f / dn;
-                        fu = nu * r; fv = nv * r; w2 = r * r;
+            bp_accumulate_angle<CONE, BP_ZPT, BP_PITCH>(P, loc[j], (uint32_t)__cvta_generic_to_shared(buf[j]), a0 + j,
+                                                        dx, dy, dz0, row_pitch, acc);
+        }
+    }
+    if (in_xy) bp_store<BP_ZPT>(P, x, y, z0, acc);
+}
+
+// ---------------------------------------------------------------------------
+// TMA-staged, warp-specialised variant (the default when the projection array
+// satisfies TMA's alignment rules: 16-byte aligned base, det_u % 4 == 0).
+//
+//   warp 8 (producer): per angle, projects the tile's corners (fp64), writes the
+//       tile-local map, and has the TMA engine copy the footprint box
+//       proj[v_lo : v_lo+WV, angle, u_lo : u_lo+64] into a ring stage
+//       (cp.async.bulk.tensor.3d; out-of-detector elements arrive as zeros,
+//       which is exactly the projector's border rule).
+//   warps 0-7 (consumers): wait on the stage's "full" mbarrier, accumulate the
+//       angle into their register-resident z runs, release the stage.
+// No block-wide barrier and no staging instructions in the compute warps.
+constexpr int BP_TMA_PITCH = 64;           // box width in elements = row pitch in shared memory
+constexpr int BP_TMA_CONSUMERS = BP_TX * BP_TY;
+constexpr int BP_TMA_THREADS = BP_TMA_CONSUMERS + 32;
+__host__ __device__ constexpr int bp_tma_stages(int zpt) { return zpt >= 16 ? 6 : 8; }
+__host__ __device__ constexpr size_t bp_tma_stage_bytes(int zpt) { return (size_t)bp_wv(zpt) * BP_TMA_PITCH * 4; }
+__host__ __device__ constexpr size_t bp_tma_smem_bytes(int zpt)
+{
+    return bp_tma_stages(zpt) * (bp_tma_stage_bytes(zpt) + sizeof(BPLocal) + 16) + 128;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+__device__ __forceinline__ void tma_load_box_3d(void *dst, const void *tmap, int c0, int c1, int c2, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        : "memory");
+}
+
+template <bool CONE, int ZPT>
+__global__ void __launch_bounds__(BP_TMA_THREADS, 3) bp_tma_kernel(const BPArgs P, const TensorMapBlob *__restrict__ tmap)
+{
+    constexpr int WV = bp_wv(ZPT);
+    constexpr int STAGES = bp_tma_stages(ZPT);
+    constexpr uint32_t STAGE_BYTES = (uint32_t)bp_tma_stage_bytes(ZPT);
+
+    extern __shared__ __align__(128) unsigned char bp_tma_smem[];
+    // carve: [stages x footprint] [stages x BPLocal] [full barriers] [empty barriers]
+    unsigned char *base = (unsigned char *)(((uintptr_t)bp_tma_smem + 127) & ~(uintptr_t)127);
+    float *bufs = reinterpret_cast<float *>(base);
+    BPLocal *loc = reinterpret_cast<BPLocal *>(base + (size_t)STAGES * STAGE_BYTES);
+    uint64_t *full = reinterpret_cast<uint64_t *>(loc + STAGES);
+    uint64_t *empty = full + STAGES;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int x0 = blockIdx.x * BP_TX, y0 = blockIdx.y * BP_TY, z0 = blockIdx.z * ZPT;
+    // z is not clipped to the volume: every thread walks its whole z run (only the store is guarded)
+    const int x1 = min(x0 + BP_TX, P.nx) - 1, y1 = min(y0 + BP_TY, P.ny) - 1, z1 = z0 + ZPT - 1;
+    const double xc = 0.5 * (x0 + x1) + 0.5 - 0.5 * P.nx, hx = 0.5 * (x1 - x0);
+    const double yc = 0.5 * (y0 + y1) + 0.5 - 0.5 * P.ny, hy = 0.5 * (y1 - y0);
+    const double zc = 0.5 * (z0 + z1) + 0.5 - 0.5 * P.nz, hz = 0.5 * (z1 - z0);
+
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(&full[s], 1);                       // the producer's arrive(+expect_tx)
+            mbar_init(&empty[s], BP_TMA_CONSUMERS / 32);  // one arrival per consumer warp
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == BP_TMA_CONSUMERS / 32) {
+        // ------------------------------------------------------------ producer
+        const int group = lane >> 3, corner = lane & 7;
+        for (int a0 = 0; a0 < P.n_angles; a0 += 4) {
+            const int a = min(a0 + group, P.n_angles - 1);
+            BPLocal L;
+            bp_setup(P, P.angles + a, corner, xc, yc, zc, hx, hy, hz, WV, 4, &L);  // valid in corner-0 lanes
+            for (int g = 0; g < 4 && a0 + g < P.n_angles; ++g) {
+                const int angle = a0 + g;
+                const int s = angle % STAGES;
+                const uint32_t round = (uint32_t)(angle / STAGES);
+                mbar_wait(&empty[s], (round & 1u) ^ 1u);  // passes immediately in round 0
+                if (lane == g * 8) {
+                    loc[s] = L;
+                    if (L.mode == BP_SMEM || L.mode == BP_SMEM_CLAMP) {
+                        mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
+                        tma_load_box_3d(bufs + (size_t)s * (STAGE_BYTES / 4), tmap, L.u_lo, angle, L.v_lo, &full[s]);
                     } else {
-                        fu = nu; fv = nv; w2 = wpar;
+                        mbar_arrive(&full[s]);
                     }
-                    const float val = bp_sample_global(src, P.det_u, P.det_v, row_pitch, fu, fv);
-                    if (val != 0.0f) acc[i] = fmaf(w2, val, acc[i]);
-                    nu += su; nv += sv;
-                    if (CONE) dn += sd;
                 }
+                __syncwarp();
             }
         }
+        return;
     }
-    if (!in_xy) return;
+
+    // --------------------------------------------------------------- consumers
+    const int tx = lane, ty = warp;
+    const int x = x0 + tx, y = y0 + ty;
+    const float dx = (float)((double)x + 0.5 - 0.5 * P.nx - xc);
+    const float dy = (float)((double)y + 0.5 - 0.5 * P.ny - yc);
+    const float dz0 = (float)((double)z0 + 0.5 - 0.5 * P.nz - zc);
+    const bool in_xy = (x < P.nx) && (y < P.ny);
+    const size_t row_pitch = (size_t)P.n_angles * P.det_u;
+
+    float acc[ZPT];
 #pragma unroll
-    for (int i = 0; i < BP_ZPT; ++i) {
-        const int z = z0 + i;
-        if (z < P.nz) {
-            float *dst = P.vol + ((size_t)z * P.ny + y) * P.nx + x;
-            const float v = acc[i] * P.out_scale;
-            *dst = P.additive ? *dst + v : v;
-        }
+    for (int i = 0; i < ZPT; ++i) acc[i] = 0.0f;
+
+    for (int angle = 0; angle < P.n_angles; ++angle) {
+        const int s = angle % STAGES;
+        const uint32_t round = (uint32_t)(angle / STAGES);
+        mbar_wait(&full[s], round & 1u);
+        if (in_xy)
+            bp_accumulate_angle<CONE, ZPT, BP_TMA_PITCH>(P, loc[s], smem_u32(bufs + (size_t)s * (STAGE_BYTES / 4)), angle,
+                                                         dx, dy, dz0, row_pitch, acc);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[s]);
     }
+    if (in_xy) bp_store<ZPT>(P, x, y, z0, acc);
 }
 
 // Voxel supersampling (rare, API parity with VoxelSuperSampling > 1): one

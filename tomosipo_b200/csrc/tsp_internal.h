@@ -43,7 +43,13 @@ struct FPGroup {
     std::vector<int> angles;
 };
 
+// The tensor map is an opaque 128-byte, 64-byte aligned CUtensorMap.
+struct alignas(64) TensorMapBlob { unsigned char bytes[128]; };
+
 struct DeviceState {
+    static constexpr unsigned kTmapSlots = 256;
+    TensorMapBlob *tmap_ring = nullptr;  // device copies of TMA descriptors
+    unsigned tmap_next = 0;
     FPAngle *fp_angles = nullptr;  // [n_angles], permuted per angle
     int *fp_lists = nullptr;       // concatenated group lists
     BPAngle *bp_angles = nullptr;  // [n_angles]

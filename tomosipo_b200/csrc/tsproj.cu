@@ -4,6 +4,7 @@
 // (SURVEY.md B.0), pick one marching axis per angle, group angles by
 // (marching axis, volume layout), and derive the affine voxel->detector maps
 // for the backprojector.
+#include <cuda.h>
 #include <cuda_runtime.h>
 
 #include <cmath>
@@ -200,6 +201,7 @@ static void free_device_state(tsp_projector *pr)
         cudaFree(kv.second.fp_angles);
         cudaFree(kv.second.fp_lists);
         cudaFree(kv.second.bp_angles);
+        cudaFree(kv.second.tmap_ring);
     }
     cudaSetDevice(cur);
     pr->dev.clear();
@@ -263,6 +265,7 @@ static int get_device_state(tsp_projector *pr, int device, DeviceState **out)
     CUDA_TRY(cudaMalloc(&st.fp_angles, A * sizeof(FPAngle)));
     CUDA_TRY(cudaMalloc(&st.bp_angles, A * sizeof(BPAngle)));
     CUDA_TRY(cudaMalloc(&st.fp_lists, A * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&st.tmap_ring, DeviceState::kTmapSlots * sizeof(TensorMapBlob)));
     CUDA_TRY(cudaMemcpy(st.fp_angles, pr->fp_angles.data(), A * sizeof(FPAngle), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(st.bp_angles, pr->bp_angles.data(), A * sizeof(BPAngle), cudaMemcpyHostToDevice));
     std::vector<int> lists;
@@ -388,6 +391,79 @@ static int launch_bp_variant(bool cone, int zpt, dim3 grid, dim3 block, cudaStre
     return fail(TSP_ERR_INVALID, "unsupported z run %d", zpt);
 }
 
+// ------------------------------------------------------------ TMA staging --
+typedef CUresult (*PFN_tensorMapEncodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                             const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                             CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                             CUtensorMapFloatOOBfill);
+
+static PFN_tensorMapEncodeTiled tensor_map_encoder()
+{
+    static PFN_tensorMapEncodeTiled fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = (PFN_tensorMapEncodeTiled)p;
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+
+// Tensor map over the projection stack viewed as (u, angle, v), box = 64 x 1 x rows.
+static bool make_proj_tensor_map(const float *proj, int det_u, int n_angles, int det_v, int box_rows, TensorMapBlob *out)
+{
+    static_assert(sizeof(CUtensorMap) == sizeof(TensorMapBlob), "CUtensorMap is 128 bytes");
+    PFN_tensorMapEncodeTiled enc = tensor_map_encoder();
+    if (!enc) return false;
+    if ((reinterpret_cast<uintptr_t>(proj) & 15u) != 0 || (det_u & 3) != 0) return false;
+    const cuuint64_t dims[3] = {(cuuint64_t)det_u, (cuuint64_t)n_angles, (cuuint64_t)det_v};
+    const cuuint64_t strides[2] = {(cuuint64_t)det_u * 4, (cuuint64_t)det_u * 4 * (cuuint64_t)n_angles};
+    const cuuint32_t box[3] = {(cuuint32_t)BP_TMA_PITCH, 1u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[3] = {1u, 1u, 1u};
+    if (strides[1] >= (1ull << 40)) return false;
+    CUresult r = enc(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(proj),
+                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS;
+}
+
+template <bool CONE, int ZPT>
+static int launch_bp_tma_one(dim3 grid, cudaStream_t stream, const BPArgs &P, const TensorMapBlob *tmap)
+{
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const size_t smem = bp_tma_smem_bytes(ZPT);
+    if (dev < 64 && !configured[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(bp_tma_kernel<CONE, ZPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev] = true;
+    }
+    bp_tma_kernel<CONE, ZPT><<<grid, BP_TMA_THREADS, smem, stream>>>(P, tmap);
+    return TSP_OK;
+}
+
+static int launch_bp_tma_variant(bool cone, int zpt, dim3 grid, cudaStream_t stream, const BPArgs &P,
+                                 const TensorMapBlob *tmap)
+{
+#define TSP_BP_CASE(Z)                                                             \
+    case Z:                                                                        \
+        return cone ? launch_bp_tma_one<true, Z>(grid, stream, P, tmap)            \
+                    : launch_bp_tma_one<false, Z>(grid, stream, P, tmap);
+    switch (zpt) {
+        TSP_BP_CASE(1)
+        TSP_BP_CASE(4)
+        TSP_BP_CASE(8)
+        TSP_BP_CASE(16)
+    }
+#undef TSP_BP_CASE
+    return fail(TSP_ERR_INVALID, "unsupported z run %d", zpt);
+}
+
 static int launch_bp(tsp_projector *pr, DeviceState *st, float *vol, const float *proj, int additive,
                      cudaStream_t stream)
 {
@@ -401,6 +477,7 @@ static int launch_bp(tsp_projector *pr, DeviceState *st, float *vol, const float
     P.additive = additive;
     P.vox_ss = g.voxel_supersampling;
     const bool cone = g.kind == TSP_KIND_CONE_VEC;
+    int used_tma = 0;
     if (g.voxel_supersampling > 1) {
         if (g.nz > 65535) return fail(TSP_ERR_INVALID, "voxel supersampling supports nz <= 65535");
         dim3 grid((g.nx + 31) / 32, (g.ny + 7) / 8, g.nz), block(32, 8);
@@ -412,10 +489,22 @@ static int launch_bp(tsp_projector *pr, DeviceState *st, float *vol, const float
         const int gy = (g.ny + BP_TY - 1) / BP_TY;
         if (gz > 65535 || gy > 65535) return fail(TSP_ERR_INVALID, "volume too large for the BP grid");
         dim3 grid((g.nx + BP_TX - 1) / BP_TX, gy, gz), block(BP_TX, BP_TY);
-        if (int rc = launch_bp_variant(cone, zpt, grid, block, stream, P)) return rc;
+        TensorMapBlob tmap;
+        const bool use_tma = !getenv("TSP_BP_NO_TMA") &&
+                             make_proj_tensor_map(proj, g.det_cols, g.n_angles, g.det_rows, bp_wv(zpt), &tmap);
+        if (use_tma) {
+            // The descriptor lives in device memory (a small ring per device, so that
+            // back-to-back asynchronous calls never overwrite a descriptor in use).
+            TensorMapBlob *slot = st->tmap_ring + (st->tmap_next++ % DeviceState::kTmapSlots);
+            CUDA_TRY(cudaMemcpyAsync(slot, &tmap, sizeof tmap, cudaMemcpyHostToDevice, stream));
+            if (int rc = launch_bp_tma_variant(cone, zpt, grid, stream, P, slot)) return rc;
+        } else {
+            if (int rc = launch_bp_variant(cone, zpt, grid, block, stream, P)) return rc;
+        }
+        used_tma = use_tma ? 1 : 0;
     }
     ++pr->launches;
-    pr->bp_uses_tma = 0;
+    pr->bp_uses_tma = used_tma;
     CUDA_TRY(cudaGetLastError());
     return TSP_OK;
 }
