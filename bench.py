@@ -36,14 +36,13 @@ UNIT = "GUPS"
 
 
 def workload(n=512, n_angles=720):
-    """cfg 3 geometry as ASTRA-style vectors."""
-    from oracle import oracle as O  # geometry helper only (restated geom_2vec)
+    """cfg 3: ts.volume(shape=n, size=1) and the cone_vec geometry
+    ts.cone(angles, shape=(n, 1.5 n), size=(1.875, 2.8125), SOD 4, SDD 6).to_vec()."""
+    import tomosipo_b200 as ts
 
-    det = (n, 3 * n // 2)
-    ang = np.linspace(0, 2 * np.pi, n_angles, endpoint=False)
-    vec = O.cone_vectors(ang, 2.8125 / det[1], 1.875 / det[0], 4.0, 2.0)
-    window = [(-0.5, 0.5)] * 3
-    return dict(kind=0, vol_shape=(n, n, n), window=window, det_shape=det, vectors=vec)
+    vg = ts.volume(shape=n, size=1)
+    pg = ts.cone(angles=n_angles, shape=(n, 3 * n // 2), size=(1.875, 2.8125), src_orig_dist=4, src_det_dist=6).to_vec()
+    return vg, pg
 
 
 def load_peaks():
@@ -109,9 +108,9 @@ def cpu_sample(n=192, n_angles=96, repeats=1):
     """Bounded CPU sample of the same workload: (n^3, n_angles, n x 1.5n)."""
     from oracle import oracle as O
 
-    w = workload(n, n_angles)
-    Q = O.OracleProjector(w["kind"], w["vol_shape"], [a for a, _ in w["window"]], [b for _, b in w["window"]],
-                          w["det_shape"], w["vectors"])
+    det = (n, 3 * n // 2)
+    vec = O.cone_vectors(np.linspace(0, 2 * np.pi, n_angles, endpoint=False), 2.8125 / det[1], 1.875 / det[0], 4.0, 2.0)
+    Q = O.OracleProjector(O.CONE_VEC, (n, n, n), [-0.5] * 3, [0.5] * 3, det, vec)
     x = O.hollow_box(n)
     y = np.zeros(Q.proj_shape, np.float32)
     xb = np.zeros(Q.vol_shape, np.float32)
@@ -138,7 +137,6 @@ def run_reference(args):
         g, dt, sample = cpu_sample()
         vals.append(g); ms.append(dt * 1e3)
     v = float(np.mean(vals))
-    w = workload()
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "strong",
@@ -156,7 +154,7 @@ def run_ours(args):
     import torch
     import torch.distributed as dist
 
-    from tomosipo_b200 import _backend as B
+    import tomosipo_b200 as ts
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -168,32 +166,30 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    w = workload()
-    n = w["vol_shape"][0]
-    n_angles = w["vectors"].shape[0]
-    # N > 1: angle-sharded FP (replicated volume), angle-sharded BP + reduce-scatter
+    vg, pg = workload()
+    n = vg.shape[0]
+    n_angles = pg.num_angles
+    # N > 1: angle-sharded FP on the replicated volume; angle-sharded BP, partial volumes
+    # combined by reduce_scatter into z-slabs and re-replicated by all_gather for the next FP
     a_lo, a_hi = rank * n_angles // world, (rank + 1) * n_angles // world
-    vec = w["vectors"][a_lo:a_hi]
-    P = B.Projector(w["kind"], w["vol_shape"], w["window"], w["det_shape"], vec)
-    from oracle import oracle as O
-    x = torch.from_numpy(O.hollow_box(n)).to(dev)
-    y = torch.empty(P.proj_shape, device=dev, dtype=torch.float32)
-    xb = torch.empty(P.vol_shape, device=dev, dtype=torch.float32)
-    xs = torch.empty((n // world,) + tuple(P.vol_shape[1:]), device=dev) if world > 1 else None
-    stream = torch.cuda.current_stream().cuda_stream
+    A = ts.operator(vg, pg[a_lo:a_hi])
+    P = A.astra_projector
+    x = torch.from_numpy(ts.phantom.hollow_box(ts.data(vg)).data).to(dev)
+    y = torch.empty(A.range_shape, device=dev, dtype=torch.float32)
+    xb = torch.empty(A.domain_shape, device=dev, dtype=torch.float32)
+    xs = torch.empty((n // world,) + tuple(A.domain_shape[1:]), device=dev) if world > 1 else None
 
-    def step():
-        P.project(B.FP, False, x.data_ptr(), y.data_ptr(), B.MEM_DEVICE, local, stream)
-        P.project(B.BP, False, xb.data_ptr(), y.data_ptr(), B.MEM_DEVICE, local, stream)
+    def exchange():
         if world > 1:
             dist.reduce_scatter_tensor(xs, xb)      # partial volumes -> z-slabs
-            dist.all_gather_into_tensor(xb, xs)     # z-slabs -> replicated volume for the next FP
+            dist.all_gather_into_tensor(xb, xs)     # z-slabs -> replicated volume
 
     for _ in range(max(args.warmup, 3)):
-        step()
+        A(x, out=y)
+        A.T(y, out=xb)
+        exchange()
     torch.cuda.synchronize()
 
-    # per-call timings for the roofline (FP call / BP call), same stream
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     launches0 = P.info().kernel_launches
     sampler = ClockSampler(local)
@@ -206,13 +202,11 @@ def run_ours(args):
     t_begin.record()
     for i in range(args.steps):
         ev[i][0].record()
-        P.project(B.FP, False, x.data_ptr(), y.data_ptr(), B.MEM_DEVICE, local, stream)
+        A(x, out=y)
         ev[i][1].record()
-        P.project(B.BP, False, xb.data_ptr(), y.data_ptr(), B.MEM_DEVICE, local, stream)
+        A.T(y, out=xb)
         ev[i][2].record()
-        if world > 1:
-            dist.reduce_scatter_tensor(xs, xb)
-            dist.all_gather_into_tensor(xb, xs)
+        exchange()
     t_end.record()
     torch.cuda.synchronize()
     if world > 1:
@@ -230,14 +224,14 @@ def run_ours(args):
     updates_step = 2.0 * n ** 3 * n_angles  # whole job, FP + BP
     value = updates_step * args.steps / (total_ms * 1e-3) / 1e9
 
-    # ---- end-to-end through the host-array path (pinned host buffers)
-    xh = torch.from_numpy(O.hollow_box(n)).pin_memory()
-    yh = torch.empty(P.proj_shape, dtype=torch.float32).pin_memory()
-    xbh = torch.empty(P.vol_shape, dtype=torch.float32).pin_memory()
+    # ---- end to end: the call a user makes, A(x) / A.T(y) on pinned HOST arrays
+    xh = torch.from_numpy(ts.phantom.hollow_box(ts.data(vg)).data).pin_memory().numpy()
+    yh = torch.empty(A.range_shape, dtype=torch.float32).pin_memory().numpy()
+    xbh = torch.empty(A.domain_shape, dtype=torch.float32).pin_memory().numpy()
 
     def e2e_step():
-        P.project(B.FP, False, xh.data_ptr(), yh.data_ptr(), B.MEM_HOST, local, stream)
-        P.project(B.BP, False, xbh.data_ptr(), yh.data_ptr(), B.MEM_HOST, local, stream)
+        A(xh, out=yh)
+        A.T(yh, out=xbh)
         return float(xbh[n // 2, n // 2, n // 2])
 
     e2e_steps = max(1, min(args.steps, 3))
