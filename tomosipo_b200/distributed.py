@@ -115,6 +115,8 @@ class ShardedOperator:
         """``y_block = A[angle block] (all_gather(x_slab))``."""
         if tuple(x_slab.shape) != self.slab_shape:
             raise ValueError(f"Expected a padded z-slab of shape {self.slab_shape}. Got {tuple(x_slab.shape)}")
+        if self.world == 1:
+            return self.local(x_slab, out=out)
         full = self._full_volume(x_slab)
         self._all_gather(full, x_slab)
         if out is None:
@@ -126,6 +128,8 @@ class ShardedOperator:
         """``x_slab = reduce_scatter(A[angle block]^T y_block)``."""
         if tuple(y_block.shape) != self.proj_shape:
             raise ValueError(f"Expected an angle block of shape {self.proj_shape}. Got {tuple(y_block.shape)}")
+        if self.world == 1:
+            return self.local.T(y_block, out=out)
         full = self._full_volume(y_block)
         if self.padded_shape != self.vol_shape:
             full[self.vol_shape[0]:].zero_()
