@@ -203,6 +203,157 @@ __global__ void __launch_bounds__(FP_BU *FP_BV) fp_kernel(const FPArgs P)
     }
 }
 
+// ---------------------------------------------------------------------------
+// Column-coherent variant: when the detector's v vector has no component along
+// the marching axis or the contiguous in-slice axis p (every circular geometry:
+// v parallel to the rotation axis), all pixels of one detector column share the
+// in-slice p coordinate, its weight and its address part for every slice.  One
+// thread then walks R consecutive rows of a column together: the p part is
+// computed once per slice, each ray only adds its q (row) part and the taps.
+constexpr int FP_COLS_R = 4;
+
+__device__ __forceinline__ void careful_range(const FPArgs &P, float ap, float aq, float cp, float cq, float t0,
+                                              int k_begin, int k_end, float &acc)
+{
+    const float *__restrict__ vol = P.vol;
+    const long long sm = P.stride_m, sq = P.stride_q;
+    for (int k = k_begin; k < k_end; ++k) {
+        const float t = (float)k + t0;
+        const float fp = fmaf(ap, t, cp), fq = fmaf(aq, t, cq);
+        const float flp = floorf(fp), flq = floorf(fq);
+        const int ip = (int)flp, iq = (int)flq;
+        const float wp = fp - flp, wq = fq - flq;
+        const bool p0 = (ip >= 0) && (ip < P.n_p), p1 = (ip >= -1) && (ip + 1 < P.n_p);
+        const bool q0 = (iq >= 0) && (iq < P.n_q), q1 = (iq >= -1) && (iq + 1 < P.n_q);
+        const float *s = vol + (long long)k * sm + (long long)iq * sq + ip;
+        const float v00 = (p0 && q0) ? __ldg(s) : 0.0f;
+        const float v10 = (p1 && q0) ? __ldg(s + 1) : 0.0f;
+        const float v01 = (p0 && q1) ? __ldg(s + sq) : 0.0f;
+        const float v11 = (p1 && q1) ? __ldg(s + sq + 1) : 0.0f;
+        const float lo = fmaf(wp, v10 - v00, v00);
+        const float hi = fmaf(wp, v11 - v01, v01);
+        acc += fmaf(wq, hi - lo, lo);
+    }
+}
+
+template <bool CONE>
+__global__ void __launch_bounds__(FP_BU * FP_BV) fp_cols_kernel(const FPArgs P)
+{
+    constexpr int R = FP_COLS_R;
+    const int a = P.list[blockIdx.y];
+    const FPAngle g = P.angles[a];
+    const int lane = threadIdx.x;
+    const int iu = blockIdx.x * FP_BU + lane;
+    const int iv0 = (blockIdx.z * FP_BV + threadIdx.y) * R;
+    const bool live_u = iu < P.det_u;
+    const float t0 = 0.5f - 0.5f * (float)P.n_m;
+
+    // shared (march, p) part of the column; per-row q part (fp64 set-up)
+    const double cu = (double)iu + 0.5, cv0 = (double)iv0 + 0.5;
+    const double pm = g.d0[0] + cu * g.u[0] + cv0 * g.v[0];
+    const double pp = g.d0[1] + cu * g.u[1] + cv0 * g.v[1];
+    const double pq0 = g.d0[2] + cu * g.u[2] + cv0 * g.v[2];
+    const double dir_m = CONE ? pm - g.o[0] : g.o[0];
+    const double dir_p = CONE ? pp - g.o[1] : g.o[1];
+    const double org_m = CONE ? g.o[0] : pm;
+    const double org_p = CONE ? g.o[1] : pp;
+    const double inv = 1.0 / dir_m;
+    const double a_p = dir_p * inv;
+    float ap = (float)a_p;
+    float cp = (float)(org_p - a_p * org_m + 0.5 * P.n_p - 0.5);
+
+    float aq[R], cq[R], scale[R], acc[R];
+    bool live[R];
+    int k_lo = P.n_m, k_hi = 0, in_lo = 0, in_hi = P.n_m;
+    float pf, pl, pif, pil;  // p-range: touch [pf, pl], interior [pif, pil]
+    k_interval(ap, cp, t0, -1.0f, (float)P.n_p, pf, pl);
+    k_interval(ap, cp, t0, 1.0f, (float)P.n_p - 2.0f, pif, pil);
+    bool any_live = false;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const double pq = pq0 + (double)r * g.v[2];
+        const double dir_q = CONE ? pq - g.o[2] : g.o[2];
+        const double org_q = CONE ? g.o[2] : pq;
+        const double a_q = dir_q * inv;
+        aq[r] = (float)a_q;
+        cq[r] = (float)(org_q - a_q * org_m + 0.5 * P.n_q - 0.5);
+        scale[r] = P.sigma_m * sqrtf(1.0f + ap * ap * P.rp2 + aq[r] * aq[r] * P.rq2);
+        acc[r] = 0.0f;
+        live[r] = live_u && (iv0 + r < P.det_v);
+        if (live[r]) {
+            float f2, l2;
+            k_interval(aq[r], cq[r], t0, -1.0f, (float)P.n_q, f2, l2);
+            const int lo = clamp_f2i(fmaxf(pf, f2) - 1.0f, 0, P.n_m, false);
+            const int hi = clamp_f2i(fminf(pl, l2) + 1.0f, 0, P.n_m, true);
+            if (hi <= lo) {
+                live[r] = false;
+            } else {
+                k_lo = min(k_lo, lo);
+                k_hi = max(k_hi, hi);
+                k_interval(aq[r], cq[r], t0, 1.0f, (float)P.n_q - 2.0f, f2, l2);
+                int ilo = clamp_f2i(fmaxf(pif, f2), 0, P.n_m, true);
+                int ihi = clamp_f2i(fminf(pil, l2), -1, P.n_m - 1, false) + 1;
+                if (P.n_p < 4 || P.n_q < 4 || ihi <= ilo || !P.offsets_fit_32bit) { ilo = P.n_m; ihi = 0; }
+                in_lo = max(in_lo, ilo);
+                in_hi = min(in_hi, ihi);
+                any_live = true;
+            }
+        }
+        if (!live[r]) { aq[r] = 0.0f; cq[r] = 1.0f; }  // dummy row: stays on an interior voxel
+    }
+    if (!any_live) { ap = 0.0f; cp = 1.0f; }          // dummy column
+    const int kA = warp_min_i(k_lo);
+    const int kD = warp_max_i(k_hi);
+    if (kD > kA) {
+        int kB = max(warp_max_i(in_lo), kA);
+        int kC = min(warp_min_i(in_hi), kD);
+        if (kB >= kC) { kB = kD; kC = kD; }
+#pragma unroll
+        for (int r = 0; r < R; ++r) careful_range(P, ap, aq[r], cp, cq[r], t0, kA, kB, acc[r]);
+        {
+            const float MAGIC = 12582912.0f;
+            const uint32_t MBITS = 0x4B400000u;
+            const float *__restrict__ vol = P.vol;
+            const uint32_t sq32 = (uint32_t)P.stride_q, sm32 = (uint32_t)P.stride_m;
+            uint32_t koff = (uint32_t)kB * sm32 - MBITS * (sq32 + 1u);
+            float t = (float)kB + t0;
+#pragma unroll 2
+            for (int k = kB; k < kC; ++k) {
+                const float fp = fmaf(ap, t, cp);
+                const float rp = __fadd_rd(fp, MAGIC);
+                const float wp = fp - (rp - MAGIC);
+                const uint32_t offp = __float_as_uint(rp) + koff;
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float fq = fmaf(aq[r], t, cq[r]);
+                    const float rq = __fadd_rd(fq, MAGIC);
+                    const float wq = fq - (rq - MAGIC);
+                    const uint32_t off = __float_as_uint(rq) * sq32 + offp;
+                    const float *s0 = vol + off;
+                    const float *s1 = vol + (off + sq32);
+                    const float v00 = __ldg(s0), v10 = __ldg(s0 + 1);
+                    const float v01 = __ldg(s1), v11 = __ldg(s1 + 1);
+                    const float lo = fmaf(wp, v10 - v00, v00);
+                    const float hi = fmaf(wp, v11 - v01, v01);
+                    acc[r] += fmaf(wq, hi - lo, lo);
+                }
+                t += 1.0f;
+                koff += sm32;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) careful_range(P, ap, aq[r], cp, cq[r], t0, kC, kD, acc[r]);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        if (live_u && iv0 + r < P.det_v) {
+            const float val = live[r] ? acc[r] * scale[r] : 0.0f;
+            float *dst = P.proj + ((size_t)(iv0 + r) * P.n_angles + a) * P.det_u + iu;
+            *dst = P.additive ? *dst + val : val;
+        }
+    }
+}
+
 // out[z][x][y] = in[z][y][x]
 __global__ void __launch_bounds__(256) transpose_xy_kernel(const float *__restrict__ in,
                                                             float *__restrict__ out, int nx, int ny)

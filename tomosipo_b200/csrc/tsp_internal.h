@@ -40,6 +40,7 @@ struct FPGroup {
     int march;           // 0 x, 1 y, 2 z  (volume axis marched)
     int p_axis, q_axis;  // in-slice axes; p is the memory-contiguous one
     bool transposed;     // reads the (z, x, y) copy instead of (z, y, x)
+    bool columns;        // det_v is parallel to the q axis: fp_cols_kernel applies
     std::vector<int> angles;
 };
 

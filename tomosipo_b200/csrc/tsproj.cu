@@ -174,8 +174,11 @@ extern "C" int tsp_projector_create(const tsp_geometry *geometry, tsp_projector 
             p = transposed ? 1 : 0;
             q = transposed ? 0 : 1;
         }
-        FPGroup &grp = groups[m * 2 + (transposed ? 1 : 0)];
-        grp.march = m; grp.p_axis = p; grp.q_axis = q; grp.transposed = transposed;
+        // detector rows parallel to the q axis: all pixels of a column share their (march, p) part
+        const double vn = std::sqrt(na.v[0] * na.v[0] + na.v[1] * na.v[1] + na.v[2] * na.v[2]);
+        const bool columns = (std::fabs(na.v[m]) + std::fabs(na.v[p])) <= 1e-12 * vn && !getenv("TSP_FP_NO_COLS");
+        FPGroup &grp = groups[(m * 2 + (transposed ? 1 : 0)) * 2 + (columns ? 1 : 0)];
+        grp.march = m; grp.p_axis = p; grp.q_axis = q; grp.transposed = transposed; grp.columns = columns;
         grp.angles.push_back(a);
         FPAngle &f = pr->fp_angles[a];
         const int perm[3] = {m, p, q};
@@ -332,8 +335,16 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
             const int na = (int)std::min<size_t>(65535, grp.angles.size() - off);
             FPArgs Q = P;
             Q.list = P.list + off;
-            dim3 grid((g.det_cols + FP_BU - 1) / FP_BU, na, (g.det_rows + FP_BV - 1) / FP_BV);
             dim3 block(FP_BU, FP_BV);
+            if (grp.columns && !ss) {
+                const int rows_per_cta = FP_BV * FP_COLS_R;
+                dim3 cgrid((g.det_cols + FP_BU - 1) / FP_BU, na, (g.det_rows + rows_per_cta - 1) / rows_per_cta);
+                if (cone) fp_cols_kernel<true><<<cgrid, block, 0, stream>>>(Q);
+                else fp_cols_kernel<false><<<cgrid, block, 0, stream>>>(Q);
+                ++pr->launches;
+                continue;
+            }
+            dim3 grid((g.det_cols + FP_BU - 1) / FP_BU, na, (g.det_rows + FP_BV - 1) / FP_BV);
             if (cone && !ss) fp_kernel<true, false><<<grid, block, 0, stream>>>(Q);
             else if (cone && ss) fp_kernel<true, true><<<grid, block, 0, stream>>>(Q);
             else if (!cone && !ss) fp_kernel<false, false><<<grid, block, 0, stream>>>(Q);
