@@ -53,6 +53,7 @@ class tsp_projector_info(ctypes.Structure):
         ("kernel_launches", ctypes.c_int64),
         ("bp_uses_tma", ctypes.c_int32),
         ("fp_uses_transpose", ctypes.c_int32),
+        ("fp_uses_tma", ctypes.c_int32),
     ]
 
 

@@ -29,7 +29,8 @@ __host__ __device__ constexpr size_t bp_smem_bytes(int zpt)
 
 // BP_SMEM_CLAMP: the footprint was clipped to the detector (+4 pixel zero margin), so
 // buffer coordinates are clamped into the zero margin before sampling.
-enum { BP_SKIP = 0, BP_SMEM = 1, BP_GLOBAL = 2, BP_SMEM_CLAMP = 3 };
+// BP_SMEM_B: like BP_SMEM, staged with the alternative row pitch (see BP_TMA_PITCH_B).
+enum { BP_SKIP = 0, BP_SMEM = 1, BP_GLOBAL = 2, BP_SMEM_CLAMP = 3, BP_SMEM_B = 4 };
 
 struct BPArgs {
     const float *proj;
@@ -40,6 +41,11 @@ struct BPArgs {
     float out_scale;  // voxel volume
     int additive;
     int vox_ss;
+    // -4 * BP_MAGIC_BITS * (pitch + 1) mod 2^32 for the launched kernel's footprint pitch.  Passed
+    // as a run-time value on purpose: as a literal, ptxas re-associates it out of the address
+    // register and re-adds it in front of every shared-memory tap (3 extra instructions per update).
+    uint32_t magic_off;
+    uint32_t magic_off_b;  // same for the alternative pitch
 };
 
 // Per-(tile, angle) set-up result, tile-local: for a voxel at offset
@@ -79,7 +85,7 @@ __device__ __forceinline__ float bp_sample_global(const float *__restrict__ proj
 // box; shuffles reduce the bounding box; lane 0 writes the local map.
 __device__ __forceinline__ void bp_setup(const BPArgs &P, const BPAngle *__restrict__ ang, int corner,
                                          double xc, double yc, double zc, double hx, double hy,
-                                         double hz, int max_rows, int u_align, BPLocal *out)
+                                         double hz, int max_rows, int max_cols, int alt_cols, int u_align, BPLocal *out)
 {
     const double den_c = ang->dn[0] * xc + ang->dn[1] * yc + ang->dn[2] * zc + ang->dn[3];
     const double nu_c = ang->nu[0] * xc + ang->nu[1] * yc + ang->nu[2] * zc + ang->nu[3];
@@ -127,9 +133,17 @@ __device__ __forceinline__ void bp_setup(const BPArgs &P, const BPAngle *__restr
             v_lo = (int)floor(vmin - 0.5) - 1;
             wu = (int)floor(umax - 0.5) + 3 - u_lo;
             wv = (int)floor(vmax - 0.5) + 3 - v_lo;
-            if (wu > BP_WU || wv > max_rows) {
+            if (wu > max_cols || wv > max_rows) {
                 mode = BP_GLOBAL;
             } else {
+                // Along a warp (x) the column moves by dU/dx per lane and the row by dV/dx.  With
+                // a row pitch = +4 banks, lanes on different rows collide only if column and row
+                // move in opposite directions; with pitch = -4 banks only if they move together
+                // (scratch/bank_sim.py: 1.37 wavefronts per tap with one fixed pitch, 1.02 with
+                // the pitch chosen by this sign).  Staging picks the pitch per (tile, angle).
+                const double su = ang->nu[0] * den_c - nu_c * ang->dn[0];
+                const double sv = ang->nv[0] * den_c - nv_c * ang->dn[0];
+                if (mode == BP_SMEM && alt_cols > 0 && wu <= alt_cols && su * sv < 0.0) mode = BP_SMEM_B;
                 off_u += (double)u_lo;
                 off_v += (double)v_lo;
             }
@@ -180,10 +194,11 @@ constexpr uint32_t BP_MAGIC_BITS = 0x4B400000u;
 // `sbase` is the shared-memory byte address of the footprint buffer.
 template <bool CONE, bool CLAMP, int ZPT, int PITCH>
 __device__ __forceinline__ void bp_tile_loop(uint32_t sbase, float nu, float nv, float dn, float su, float sv,
-                                             float sd, float umax, float vmax, float wpar, float (&acc)[ZPT])
+                                             float sd, float umax, float vmax, float wpar, uint32_t magic_off,
+                                             float (&acc)[ZPT])
 {
     // byte address = sbase + 4 * ((rv_bits - M) * PITCH + (ru_bits - M))
-    const uint32_t cbase = sbase - 4u * BP_MAGIC_BITS * (uint32_t)(PITCH + 1);
+    const uint32_t cbase = sbase + magic_off;
 #pragma unroll
     for (int i = 0; i < ZPT; ++i) {
         float fu, fv, w2;
@@ -217,14 +232,14 @@ __device__ __forceinline__ void bp_tile_loop(uint32_t sbase, float nu, float nv,
 // ray-density weight are computed once per (x, y); only the row moves.
 template <bool CONE, int ZPT, int PITCH>
 __device__ __forceinline__ void bp_tile_loop_zinv(uint32_t sbase, float nu, float nv, float dn, float sv,
-                                                  float wpar, float (&acc)[ZPT])
+                                                  float wpar, uint32_t magic_off, float (&acc)[ZPT])
 {
     float r = 1.0f, w2 = wpar;
     if (CONE) { r = rcp_approx(dn); w2 = r * r; }
     const float fu = nu * r;
     const float ru = __fadd_rd(fu, BP_MAGIC);
     const float wu = fu - (ru - BP_MAGIC);
-    const uint32_t cbase = sbase - 4u * BP_MAGIC_BITS * (uint32_t)(PITCH + 1) + 4u * __float_as_uint(ru);
+    const uint32_t cbase = sbase + magic_off + 4u * __float_as_uint(ru);
     float fv = nv * r;
     const float dv = sv * r;
 #pragma unroll
@@ -244,7 +259,7 @@ __device__ __forceinline__ void bp_tile_loop_zinv(uint32_t sbase, float nu, floa
 
 // One angle's contribution to a thread's z run.  `L` lives in shared memory;
 // `sbase` is the shared byte address of the staged footprint (row pitch PITCH).
-template <bool CONE, int ZPT, int PITCH>
+template <bool CONE, int ZPT, int PITCH, int PITCH_B>
 __device__ __forceinline__ void bp_accumulate_angle(const BPArgs &P, const BPLocal &L, uint32_t sbase, int angle,
                                                     float dx, float dy, float dz0, size_t row_pitch,
                                                     float (&acc)[ZPT])
@@ -257,11 +272,14 @@ __device__ __forceinline__ void bp_accumulate_angle(const BPArgs &P, const BPLoc
     const float su = L.au[2], sv = L.av[2], sd = L.ad[2];
     const float wpar = L.weight;
     if (mode == BP_SMEM) {
-        if (L.z_invariant) bp_tile_loop_zinv<CONE, ZPT, PITCH>(sbase, nu, nv, dn, sv, wpar, acc);
-        else bp_tile_loop<CONE, false, ZPT, PITCH>(sbase, nu, nv, dn, su, sv, sd, 0.0f, 0.0f, wpar, acc);
+        if (L.z_invariant) bp_tile_loop_zinv<CONE, ZPT, PITCH>(sbase, nu, nv, dn, sv, wpar, P.magic_off, acc);
+        else bp_tile_loop<CONE, false, ZPT, PITCH>(sbase, nu, nv, dn, su, sv, sd, 0.0f, 0.0f, wpar, P.magic_off, acc);
+    } else if (PITCH_B != PITCH && mode == BP_SMEM_B) {
+        if (L.z_invariant) bp_tile_loop_zinv<CONE, ZPT, PITCH_B>(sbase, nu, nv, dn, sv, wpar, P.magic_off_b, acc);
+        else bp_tile_loop<CONE, false, ZPT, PITCH_B>(sbase, nu, nv, dn, su, sv, sd, 0.0f, 0.0f, wpar, P.magic_off_b, acc);
     } else if (mode == BP_SMEM_CLAMP) {
         bp_tile_loop<CONE, true, ZPT, PITCH>(sbase, nu, nv, dn, su, sv, sd, (float)L.wu - 1.5f, (float)L.wv - 1.5f,
-                                             wpar, acc);
+                                             wpar, P.magic_off, acc);
     } else {
         const float *src = P.proj + (size_t)angle * P.det_u;
 #pragma unroll
@@ -331,12 +349,12 @@ __global__ void __launch_bounds__(BP_THREADS) bp_kernel(const BPArgs P)
             const int j = tid >> 3;
             // clamp so that all 8 lanes of a group take part in the shuffles
             const int a = a0 + min(j, na - 1);
-            bp_setup(P, P.angles + a, tid & 7, xc, yc, zc, hx, hy, hz, BP_WV, 1, &loc[j]);
+            bp_setup(P, P.angles + a, tid & 7, xc, yc, zc, hx, hy, hz, BP_WV, BP_WU, 0, 1, &loc[j]);
         }
         __syncthreads();
         // stage footprints: warps over rows, lanes over columns
         for (int j = 0; j < na; ++j) {
-            if (loc[j].mode != BP_SMEM && loc[j].mode != BP_SMEM_CLAMP) continue;
+            if (loc[j].mode != BP_SMEM && loc[j].mode != BP_SMEM_CLAMP) continue;  // (BP_SMEM_B never occurs here)
             const int u_lo = loc[j].u_lo, v_lo = loc[j].v_lo, wu = loc[j].wu, wv = loc[j].wv;
             const float *src = P.proj + (size_t)(a0 + j) * P.det_u;
             for (int r = ty; r < wv; r += BP_TY) {
@@ -353,7 +371,7 @@ __global__ void __launch_bounds__(BP_THREADS) bp_kernel(const BPArgs P)
         __syncthreads();
         if (!in_xy) continue;
         for (int j = 0; j < na; ++j) {
-            bp_accumulate_angle<CONE, BP_ZPT, BP_PITCH>(P, loc[j], (uint32_t)__cvta_generic_to_shared(buf[j]), a0 + j,
+            bp_accumulate_angle<CONE, BP_ZPT, BP_PITCH, BP_PITCH>(P, loc[j], (uint32_t)__cvta_generic_to_shared(buf[j]), a0 + j,
                                                         dx, dy, dz0, row_pitch, acc);
         }
     }
@@ -366,36 +384,44 @@ __global__ void __launch_bounds__(BP_THREADS) bp_kernel(const BPArgs P)
 //
 //   warp 8 (producer): per angle, projects the tile's corners (fp64), writes the
 //       tile-local map, and has the TMA engine copy the footprint box
-//       proj[v_lo : v_lo+WV, angle, u_lo : u_lo+64] into a ring stage
+//       proj[v_lo : v_lo+WV, angle, u_lo : u_lo+68] into a ring stage
 //       (cp.async.bulk.tensor.3d; out-of-detector elements arrive as zeros,
 //       which is exactly the projector's border rule).
 //   warps 0-7 (consumers): wait on the stage's "full" mbarrier, accumulate the
 //       angle into their register-resident z runs, release the stage.
 // No block-wide barrier and no staging instructions in the compute warps.
-constexpr int BP_TMA_PITCH = 64;           // box width in elements = row pitch in shared memory
+// Row pitch of a staged footprint = TMA box width.  64 + 4: consecutive rows start 4 banks
+// apart, so lanes that sit in the same detector column on different rows (angles whose u
+// axis is nearly perpendicular to x) do not collide on a bank (ncu, pitch 64: 43 % excess
+// shared wavefronts on every tap).
+constexpr int BP_TMA_PITCH = 68;
+constexpr int BP_TMA_PITCH_B = 60;  // alternative: consecutive rows start 4 banks *earlier*
 constexpr int BP_TMA_CONSUMERS = BP_TX * BP_TY;
 constexpr int BP_TMA_THREADS = BP_TMA_CONSUMERS + 32;
-__host__ __device__ constexpr int bp_tma_stages(int zpt) { return zpt >= 16 ? 6 : 8; }
-__host__ __device__ constexpr size_t bp_tma_stage_bytes(int zpt) { return (size_t)bp_wv(zpt) * BP_TMA_PITCH * 4; }
+__host__ __device__ constexpr int bp_tma_stages(int zpt) { return zpt >= 32 ? 4 : (zpt >= 16 ? 6 : 8); }
+__host__ __device__ constexpr size_t bp_tma_box_bytes(int zpt) { return (size_t)bp_wv(zpt) * BP_TMA_PITCH * 4; }
+// ring stages are 128-byte aligned (TMA destination alignment)
+__host__ __device__ constexpr size_t bp_tma_stage_bytes(int zpt) { return (bp_tma_box_bytes(zpt) + 127) / 128 * 128; }
 __host__ __device__ constexpr size_t bp_tma_smem_bytes(int zpt)
 {
     return bp_tma_stages(zpt) * (bp_tma_stage_bytes(zpt) + sizeof(BPLocal) + 16) + 128;
 }
+__host__ __device__ constexpr int bp_tma_min_ctas(int zpt) { return zpt >= 32 ? 2 : 3; }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity)
 {
     uint32_t ok;
     asm volatile(
@@ -405,37 +431,42 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(bar), "r"(parity)
         : "memory");
     return ok != 0;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     while (!mbar_try_wait(bar, parity)) {
     }
 }
-__device__ __forceinline__ void tma_load_box_3d(void *dst, const void *tmap, int c0, int c1, int c2, uint64_t *bar)
+__device__ __forceinline__ void tma_load_box_3d(uint32_t dst, const void *tmap, int c0, int c1, int c2, uint32_t bar)
 {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
-        ::"r"(smem_u32(dst)), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(smem_u32(bar))
+        ::"r"(dst), "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
         : "memory");
 }
 
 template <bool CONE, int ZPT>
-__global__ void __launch_bounds__(BP_TMA_THREADS, 3) bp_tma_kernel(const BPArgs P, const TensorMapBlob *__restrict__ tmap)
+__global__ void __launch_bounds__(BP_TMA_THREADS, bp_tma_min_ctas(ZPT))
+bp_tma_kernel(const BPArgs P, const TensorMapBlob *__restrict__ tmap)  // tmap[0]: pitch 68 boxes, tmap[1]: pitch 60
 {
     constexpr int WV = bp_wv(ZPT);
     constexpr int STAGES = bp_tma_stages(ZPT);
     constexpr uint32_t STAGE_BYTES = (uint32_t)bp_tma_stage_bytes(ZPT);
+    constexpr uint32_t BOX_BYTES = (uint32_t)bp_tma_box_bytes(ZPT);
+    constexpr uint32_t BOX_BYTES_B = (uint32_t)(bp_wv(ZPT) * BP_TMA_PITCH_B * 4);
 
     extern __shared__ __align__(128) unsigned char bp_tma_smem[];
-    // carve: [stages x footprint] [stages x BPLocal] [full barriers] [empty barriers]
-    unsigned char *base = (unsigned char *)(((uintptr_t)bp_tma_smem + 127) & ~(uintptr_t)127);
-    float *bufs = reinterpret_cast<float *>(base);
+    // carve: [stages x footprint] [stages x BPLocal] [full barriers] [empty barriers];
+    // the base is aligned by an offset (not an integer round trip) so that the compiler
+    // keeps the shared state space of every pointer derived from it
+    unsigned char *base = bp_tma_smem + ((128u - (smem_u32(bp_tma_smem) & 127u)) & 127u);
     BPLocal *loc = reinterpret_cast<BPLocal *>(base + (size_t)STAGES * STAGE_BYTES);
-    uint64_t *full = reinterpret_cast<uint64_t *>(loc + STAGES);
-    uint64_t *empty = full + STAGES;
+    const uint32_t bufs = smem_u32(base);
+    const uint32_t full = smem_u32(loc + STAGES);
+    const uint32_t empty = full + 8u * STAGES;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -448,8 +479,8 @@ __global__ void __launch_bounds__(BP_TMA_THREADS, 3) bp_tma_kernel(const BPArgs 
 
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
-            mbar_init(&full[s], 1);                       // the producer's arrive(+expect_tx)
-            mbar_init(&empty[s], BP_TMA_CONSUMERS / 32);  // one arrival per consumer warp
+            mbar_init(full + 8u * s, 1);                       // the producer's arrive(+expect_tx)
+            mbar_init(empty + 8u * s, BP_TMA_CONSUMERS / 32);  // one arrival per consumer warp
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -458,25 +489,29 @@ __global__ void __launch_bounds__(BP_TMA_THREADS, 3) bp_tma_kernel(const BPArgs 
     if (warp == BP_TMA_CONSUMERS / 32) {
         // ------------------------------------------------------------ producer
         const int group = lane >> 3, corner = lane & 7;
+        int s = 0;
+        uint32_t parity = 1u;  // waiting on a fresh "empty" barrier with parity 1 passes at once
         for (int a0 = 0; a0 < P.n_angles; a0 += 4) {
             const int a = min(a0 + group, P.n_angles - 1);
             BPLocal L;
-            bp_setup(P, P.angles + a, corner, xc, yc, zc, hx, hy, hz, WV, 4, &L);  // valid in corner-0 lanes
+            bp_setup(P, P.angles + a, corner, xc, yc, zc, hx, hy, hz, WV, BP_TMA_PITCH, BP_TMA_PITCH_B, 4, &L);  // valid in corner-0 lanes
             for (int g = 0; g < 4 && a0 + g < P.n_angles; ++g) {
                 const int angle = a0 + g;
-                const int s = angle % STAGES;
-                const uint32_t round = (uint32_t)(angle / STAGES);
-                mbar_wait(&empty[s], (round & 1u) ^ 1u);  // passes immediately in round 0
+                mbar_wait(empty + 8u * s, parity);
                 if (lane == g * 8) {
                     loc[s] = L;
                     if (L.mode == BP_SMEM || L.mode == BP_SMEM_CLAMP) {
-                        mbar_arrive_expect_tx(&full[s], STAGE_BYTES);
-                        tma_load_box_3d(bufs + (size_t)s * (STAGE_BYTES / 4), tmap, L.u_lo, angle, L.v_lo, &full[s]);
+                        mbar_arrive_expect_tx(full + 8u * s, BOX_BYTES);
+                        tma_load_box_3d(bufs + (uint32_t)s * STAGE_BYTES, tmap, L.u_lo, angle, L.v_lo, full + 8u * s);
+                    } else if (L.mode == BP_SMEM_B) {
+                        mbar_arrive_expect_tx(full + 8u * s, BOX_BYTES_B);
+                        tma_load_box_3d(bufs + (uint32_t)s * STAGE_BYTES, tmap + 1, L.u_lo, angle, L.v_lo, full + 8u * s);
                     } else {
-                        mbar_arrive(&full[s]);
+                        mbar_arrive(full + 8u * s);
                     }
                 }
                 __syncwarp();
+                if (++s == STAGES) { s = 0; parity ^= 1u; }
             }
         }
         return;
@@ -495,15 +530,16 @@ __global__ void __launch_bounds__(BP_TMA_THREADS, 3) bp_tma_kernel(const BPArgs 
 #pragma unroll
     for (int i = 0; i < ZPT; ++i) acc[i] = 0.0f;
 
+    int s = 0;
+    uint32_t parity = 0u;
     for (int angle = 0; angle < P.n_angles; ++angle) {
-        const int s = angle % STAGES;
-        const uint32_t round = (uint32_t)(angle / STAGES);
-        mbar_wait(&full[s], round & 1u);
+        mbar_wait(full + 8u * s, parity);
         if (in_xy)
-            bp_accumulate_angle<CONE, ZPT, BP_TMA_PITCH>(P, loc[s], smem_u32(bufs + (size_t)s * (STAGE_BYTES / 4)), angle,
-                                                         dx, dy, dz0, row_pitch, acc);
+            bp_accumulate_angle<CONE, ZPT, BP_TMA_PITCH, BP_TMA_PITCH_B>(P, loc[s], bufs + (uint32_t)s * STAGE_BYTES, angle, dx, dy, dz0,
+                                                         row_pitch, acc);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);
+        if (lane == 0) mbar_arrive(empty + 8u * s);
+        if (++s == STAGES) { s = 0; parity ^= 1u; }
     }
     if (in_xy) bp_store<ZPT>(P, x, y, z0, acc);
 }

@@ -354,12 +354,13 @@ __global__ void __launch_bounds__(FP_BU * FP_BV) fp_cols_kernel(const FPArgs P)
     }
 }
 
-// out[z][x][y] = in[z][y][x]
+// out[z][x][y] = in[z][y][x]; the rows of `out` have pitch ny_pad >= ny
 __global__ void __launch_bounds__(256) transpose_xy_kernel(const float *__restrict__ in,
-                                                            float *__restrict__ out, int nx, int ny)
+                                                            float *__restrict__ out, int nx, int ny, int ny_pad)
 {
     __shared__ float tile[32][33];
     const size_t plane = (size_t)nx * ny * blockIdx.z;
+    const size_t plane_out = (size_t)nx * ny_pad * blockIdx.z;
     const int x0 = blockIdx.x * 32, y0 = blockIdx.y * 32;
     for (int r = threadIdx.y; r < 32; r += 8) {
         const int x = x0 + threadIdx.x, y = y0 + r;
@@ -368,7 +369,7 @@ __global__ void __launch_bounds__(256) transpose_xy_kernel(const float *__restri
     __syncthreads();
     for (int r = threadIdx.y; r < 32; r += 8) {
         const int y = y0 + threadIdx.x, x = x0 + r;
-        if (x < nx && y < ny) out[plane + (size_t)x * ny + y] = tile[threadIdx.x][r];
+        if (x < nx && y < ny) out[plane_out + (size_t)x * ny_pad + y] = tile[threadIdx.x][r];
     }
 }
 

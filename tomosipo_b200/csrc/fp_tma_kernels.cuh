@@ -1,0 +1,291 @@
+// Forward projection, TMA-staged variant (default when the volume layout meets
+// TMA's alignment rules).  Same arithmetic as fp_kernel / fp_cols_kernel
+// (Joseph march), different data path:
+//
+//   * a CTA owns a 32 (u) x 16 (v) detector tile for a PAIR of neighbouring
+//     angles and marches through the slices of the volume together;
+//   * per slice, the producer warp bounds the tile's footprint on that slice (the
+//     bounding box of the 2 x 4 corner rays, exact for projective maps) and has
+//     the TMA engine copy that box of the slice into a shared-memory ring stage;
+//     voxels outside the volume arrive as zeros, which is the projector's border
+//     rule - so there is no bounds-checked "careful" loop at all;
+//   * the 8 consumer warps (4 per angle, 4 detector rows per thread) take their
+//     four bilinear taps from shared memory (bank-granular, not line-granular
+//     like the L1 path: ncu showed the LDG kernel bound by L1 wavefronts, ~2
+//     128-byte lines per tap instruction);
+//   * two neighbouring angles share the staged box (their footprints differ by a
+//     few voxels), which halves the L2 -> shared-memory traffic per sample.
+//
+// A slice whose footprint does not fit the box (unusual geometries) is flagged by
+// the producer and sampled with bounds-checked global loads instead.
+#pragma once
+#include "bp_kernels.cuh"  // mbarrier / TMA helpers
+#include "fp_kernels.cuh"
+
+namespace tsp {
+
+constexpr int FPT_TU = 32;         // det_u pixels per CTA
+constexpr int FPT_R = 4;           // det_v rows per thread
+constexpr int FPT_TV = 4 * FPT_R;  // det_v rows per CTA (4 warps per angle)
+constexpr int FPT_CONSUMERS = 256;
+constexpr int FPT_THREADS = FPT_CONSUMERS + 32;
+
+struct FPTmaArgs {
+    FPArgs a;               // volume (for the fallback path), dims, angle table, list, output
+    const int *pairs;       // angle pairs of this launch: {a, b} with b = -1 for a single angle
+    int box_w, box_h;       // staged box, elements (box_w % 4 == 0)
+    int march_is_middle;    // tensor coordinates are (p, k, q) if set, (p, q, k) otherwise
+    int stages;
+    uint32_t stage_bytes;   // box_w * box_h * 4 rounded up to 128
+    uint32_t magic_off;     // -4 * MAGIC_BITS * (box_w + 1) mod 2^32 (run-time on purpose, see BPArgs)
+};
+
+struct FPRay {
+    float ap, cp, aq, cq;
+};
+
+// Ray through the centre-relative detector coordinate (cu, cv) of angle g, as
+// index-space lines  p(k) = ap * (k + t0) + cp,  q(k) = aq * (k + t0) + cq.
+template <bool CONE>
+__device__ __forceinline__ FPRay fpt_ray(const FPAngle &g, double cu, double cv, int n_p, int n_q)
+{
+    const double pm = g.d0[0] + cu * g.u[0] + cv * g.v[0];
+    const double pp = g.d0[1] + cu * g.u[1] + cv * g.v[1];
+    const double pq = g.d0[2] + cu * g.u[2] + cv * g.v[2];
+    const double dir_m = CONE ? pm - g.o[0] : g.o[0];
+    const double dir_p = CONE ? pp - g.o[1] : g.o[1];
+    const double dir_q = CONE ? pq - g.o[2] : g.o[2];
+    const double org_m = CONE ? g.o[0] : pm;
+    const double org_p = CONE ? g.o[1] : pp;
+    const double org_q = CONE ? g.o[2] : pq;
+    const double inv = 1.0 / dir_m;
+    const double a_p = dir_p * inv, a_q = dir_q * inv;
+    FPRay r;
+    r.ap = (float)a_p;
+    r.aq = (float)a_q;
+    r.cp = (float)(org_p - a_p * org_m + 0.5 * n_p - 0.5);
+    r.cq = (float)(org_q - a_q * org_m + 0.5 * n_q - 0.5);
+    return r;
+}
+
+template <int OFF>
+__device__ __forceinline__ float fpt_lds(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void fpt_tma_box(uint32_t dst, const void *tmap, int c0, int c1, int c2, uint32_t bar)
+{
+    tma_load_box_3d(dst, tmap, c0, c1, c2, bar);
+}
+
+// Bounding box of the 8 corner rays on slice k: [pmin, pmax] x [qmin, qmax] (index coordinates).
+__device__ __forceinline__ void fpt_slice_box(const FPRay (&c)[8], float t, float &pmin, float &pmax, float &qmin,
+                                              float &qmax)
+{
+    pmin = qmin = 3.0e38f;
+    pmax = qmax = -3.0e38f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float p = fmaf(c[i].ap, t, c[i].cp), q = fmaf(c[i].aq, t, c[i].cq);
+        pmin = fminf(pmin, p); pmax = fmaxf(pmax, p);
+        qmin = fminf(qmin, q); qmax = fmaxf(qmax, q);
+    }
+    // consumers evaluate interior rays in fp32: allow for their rounding
+    pmin -= 0.01f; qmin -= 0.01f; pmax += 0.01f; qmax += 0.01f;
+}
+
+template <bool CONE, bool COLS>
+__global__ void __launch_bounds__(FPT_THREADS, 3) fp_tma_kernel(const FPTmaArgs A, const TensorMapBlob *__restrict__ tmap)
+{
+    constexpr int R = FPT_R;
+    const FPArgs &P = A.a;
+    extern __shared__ __align__(128) unsigned char fpt_smem[];
+    unsigned char *base = fpt_smem + ((128u - (smem_u32(fpt_smem) & 127u)) & 127u);
+    const uint32_t bufs = smem_u32(base);
+    const uint32_t ctrl = bufs + (uint32_t)A.stages * A.stage_bytes;  // per stage: {uint32 sb, uint32 fit}
+    const uint32_t full = ctrl + 8u * A.stages;
+    const uint32_t empty = full + 8u * A.stages;
+    int *hull = reinterpret_cast<int *>(base + (size_t)A.stages * (A.stage_bytes + 24u));  // {kA, kD}
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int pair_a = A.pairs[2 * blockIdx.y], pair_b = A.pairs[2 * blockIdx.y + 1];
+    const int n_in_pair = pair_b >= 0 ? 2 : 1;
+    const int u0 = blockIdx.x * FPT_TU, v0 = blockIdx.z * FPT_TV;
+    const int u1 = min(u0 + FPT_TU, P.det_u) - 1, v1 = min(v0 + FPT_TV, P.det_v) - 1;
+    const float t0 = 0.5f - 0.5f * (float)P.n_m;
+
+    if (tid == 0) {
+        for (int s = 0; s < A.stages; ++s) {
+            mbar_init(full + 8u * s, 1);
+            mbar_init(empty + 8u * s, FPT_CONSUMERS / 32);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (warp == FPT_CONSUMERS / 32) {
+        // ------------------------------------------------------------ producer
+        // lanes 0..7 each trace one corner ray (angle slot = lane >> 2), then everybody gets all 8
+        FPRay mine;
+        {
+            const int slot = min((lane >> 2) & 1, n_in_pair - 1);
+            const FPAngle g = P.angles[slot ? pair_b : pair_a];
+            const double cu = (double)((lane & 1) ? u1 : u0) + 0.5;
+            const double cv = (double)((lane & 2) ? v1 : v0) + 0.5;
+            mine = fpt_ray<CONE>(g, cu, cv, P.n_p, P.n_q);
+        }
+        FPRay c[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            c[i].ap = __shfl_sync(0xffffffffu, mine.ap, i);
+            c[i].cp = __shfl_sync(0xffffffffu, mine.cp, i);
+            c[i].aq = __shfl_sync(0xffffffffu, mine.aq, i);
+            c[i].cq = __shfl_sync(0xffffffffu, mine.cq, i);
+        }
+        // hull of the slices on which the tile's footprint touches the volume
+        int kA = P.n_m, kD = 0;
+        for (int k0 = 0; k0 < P.n_m; k0 += 32) {
+            const int k = k0 + lane;
+            float pmin, pmax, qmin, qmax;
+            fpt_slice_box(c, (float)k + t0, pmin, pmax, qmin, qmax);
+            const bool needed = (k < P.n_m) && (pmax > -1.0f) && (pmin < (float)P.n_p) && (qmax > -1.0f) &&
+                                (qmin < (float)P.n_q);
+            const unsigned m = __ballot_sync(0xffffffffu, needed);
+            if (m) {
+                kA = min(kA, k0 + __ffs(m) - 1);
+                kD = max(kD, k0 + 32 - __clz(m));
+            }
+        }
+        if (kD <= kA) { kA = 0; kD = 0; }
+        if (lane == 0) { hull[0] = kA; hull[1] = kD; }
+        __syncthreads();
+
+        int s = 0;
+        uint32_t parity = 1u;
+        const uint32_t box_bytes = (uint32_t)A.box_w * (uint32_t)A.box_h * 4u;
+        for (int k0 = kA; k0 < kD; k0 += 32) {
+            const int k = k0 + lane;
+            float pmin, pmax, qmin, qmax;
+            fpt_slice_box(c, (float)k + t0, pmin, pmax, qmin, qmax);
+            // clamp far-away boxes so that the float -> int conversions are safe
+            pmin = fmaxf(pmin, -1.0e6f); qmin = fmaxf(qmin, -1.0e6f);
+            pmax = fminf(pmax, 1.0e6f); qmax = fminf(qmax, 1.0e6f);
+            int p0 = __float2int_rd(pmin);
+            p0 -= ((p0 % 4) + 4) % 4;  // TMA: innermost coordinate on a 16-byte boundary
+            const int q0 = __float2int_rd(qmin);
+            const int fit = (__float2int_rd(pmax) + 2 - p0 <= A.box_w) && (__float2int_rd(qmax) + 2 - q0 <= A.box_h) &&
+                            (pmax >= pmin) && (qmax >= qmin);
+            const int nj = min(32, kD - k0);
+            for (int j = 0; j < nj; ++j) {
+                const int p0j = __shfl_sync(0xffffffffu, p0, j);
+                const int q0j = __shfl_sync(0xffffffffu, q0, j);
+                const int fitj = __shfl_sync(0xffffffffu, fit, j);
+                mbar_wait(empty + 8u * s, parity);
+                if (lane == 0) {
+                    const uint32_t dst = bufs + (uint32_t)s * A.stage_bytes;
+                    const uint32_t sb = dst - 4u * (uint32_t)(q0j * A.box_w + p0j) + A.magic_off;
+                    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ctrl + 8u * s), "r"(sb), "r"((uint32_t)fitj)
+                                 : "memory");
+                    if (fitj) {
+                        mbar_arrive_expect_tx(full + 8u * s, box_bytes);
+                        if (A.march_is_middle) fpt_tma_box(dst, tmap, p0j, k0 + j, q0j, full + 8u * s);
+                        else fpt_tma_box(dst, tmap, p0j, q0j, k0 + j, full + 8u * s);
+                    } else {
+                        mbar_arrive(full + 8u * s);
+                    }
+                }
+                __syncwarp();
+                if (++s == A.stages) { s = 0; parity ^= 1u; }
+            }
+        }
+        return;
+    }
+
+    // --------------------------------------------------------------- consumers
+    const int slot = warp >> 2;                 // which angle of the pair
+    const bool slot_live = slot < n_in_pair;
+    const int a = slot_live && slot ? pair_b : pair_a;
+    const FPAngle g = P.angles[a];
+    const int iu = u0 + lane;
+    const int iv0 = v0 + (warp & 3) * R;
+    // out-of-detector lanes / rows shadow the tile's last pixel: their taps stay inside the staged box
+    const double cu = (double)min(iu, u1) + 0.5;
+
+    float ap[COLS ? 1 : R], cp[COLS ? 1 : R], aq[R], cq[R], acc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const double cv = (double)min(iv0 + r, v1) + 0.5;
+        const FPRay ray = fpt_ray<CONE>(g, cu, cv, P.n_p, P.n_q);
+        if (!COLS || r == 0) { ap[COLS ? 0 : r] = ray.ap; cp[COLS ? 0 : r] = ray.cp; }
+        aq[r] = ray.aq; cq[r] = ray.cq;
+        acc[r] = 0.0f;
+    }
+    __syncthreads();
+    const int kA = hull[0], kD = hull[1];
+
+    const float MAGIC = 12582912.0f;
+    const uint32_t bw4 = (uint32_t)A.box_w * 4u;
+    float t = (float)kA + t0;
+    int s = 0;
+    uint32_t parity = 0u;
+    for (int k = kA; k < kD; ++k) {
+        mbar_wait(full + 8u * s, parity);
+        uint32_t sb, fit;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(sb), "=r"(fit) : "r"(ctrl + 8u * s) : "memory");
+        if (fit) {
+            float wp = 0.0f;
+            uint32_t offp = 0u;
+            if (COLS) {
+                const float fp = fmaf(ap[0], t, cp[0]);
+                const float rp = __fadd_rd(fp, MAGIC);
+                wp = fp - (rp - MAGIC);
+                offp = __float_as_uint(rp) * 4u + sb;
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (!COLS) {
+                    const float fp = fmaf(ap[COLS ? 0 : r], t, cp[COLS ? 0 : r]);
+                    const float rp = __fadd_rd(fp, MAGIC);
+                    wp = fp - (rp - MAGIC);
+                    offp = __float_as_uint(rp) * 4u + sb;
+                }
+                const float fq = fmaf(aq[r], t, cq[r]);
+                const float rq = __fadd_rd(fq, MAGIC);
+                const float wq = fq - (rq - MAGIC);
+                const uint32_t a0 = __float_as_uint(rq) * bw4 + offp;
+                const uint32_t a1 = a0 + bw4;
+                const float v00 = fpt_lds<0>(a0), v10 = fpt_lds<4>(a0);
+                const float v01 = fpt_lds<0>(a1), v11 = fpt_lds<4>(a1);
+                const float lo = fmaf(wp, v10 - v00, v00);
+                const float hi = fmaf(wp, v11 - v01, v01);
+                acc[r] += fmaf(wq, hi - lo, lo);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                careful_range(P, ap[COLS ? 0 : r], aq[r], cp[COLS ? 0 : r], cq[r], t0, k, k + 1, acc[r]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + 8u * s);
+        if (++s == A.stages) { s = 0; parity ^= 1u; }
+        t += 1.0f;
+    }
+
+    if (slot_live && iu < P.det_u) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            if (iv0 + r < P.det_v) {
+                const float apr = ap[COLS ? 0 : r];
+                const float scale = P.sigma_m * sqrtf(1.0f + apr * apr * P.rp2 + aq[r] * aq[r] * P.rq2);
+                const float val = acc[r] * scale;
+                float *dst = P.proj + ((size_t)(iv0 + r) * P.n_angles + a) * P.det_u + iu;
+                *dst = P.additive ? *dst + val : val;
+            }
+        }
+    }
+}
+
+}  // namespace tsp

@@ -42,6 +42,10 @@ struct FPGroup {
     bool transposed;     // reads the (z, x, y) copy instead of (z, y, x)
     bool columns;        // det_v is parallel to the q axis: fp_cols_kernel applies
     std::vector<int> angles;
+    // TMA-staged kernel (fp_tma_kernel): angles paired with a neighbour whose footprint nearly
+    // coincides (second = -1: single), and the staged box that bounds every pair's footprint.
+    std::vector<int> pairs;  // 2 ints per pair
+    int box_w = 0, box_h = 0;  // 0: group not eligible
 };
 
 // The tensor map is an opaque 128-byte, 64-byte aligned CUtensorMap.
@@ -53,6 +57,8 @@ struct DeviceState {
     unsigned tmap_next = 0;
     FPAngle *fp_angles = nullptr;  // [n_angles], permuted per angle
     int *fp_lists = nullptr;       // concatenated group lists
+    int *fp_pairs = nullptr;       // concatenated group pair lists (2 ints per pair)
+    std::vector<size_t> pair_offset;  // in pairs
     BPAngle *bp_angles = nullptr;  // [n_angles]
     std::vector<size_t> list_offset;
 };
@@ -72,4 +78,5 @@ struct tsp_projector {
     int64_t launches = 0;
     int bp_uses_tma = 0;
     int fp_uses_transpose = 0;
+    int fp_uses_tma = 0;
 };

@@ -15,6 +15,7 @@
 
 #include "bp_kernels.cuh"
 #include "fp_kernels.cuh"
+#include "fp_tma_kernels.cuh"
 #include "tsp_internal.h"
 
 using namespace tsp;
@@ -116,6 +117,106 @@ static void build_bp_angle(const tsp_geometry &g, const NormAngle &n, BPAngle &o
     }
 }
 
+
+// ------------------------------------------- FP footprint boxes (TMA path) --
+// Host mirror of fpt_ray / fpt_slice_box (fp_tma_kernels.cuh): bounds, for one
+// launch group, the box that the footprint of any 32 x 16 detector tile of an
+// angle pair needs on any slice, and pairs neighbouring angles whose footprints
+// nearly coincide.  An underestimate only costs speed (the kernel flags slices
+// that do not fit and samples them from global memory).
+struct HostRay { double ap, cp, aq, cq; };
+
+static HostRay host_ray(bool cone, const FPAngle &g, double cu, double cv, int n_p, int n_q)
+{
+    const double pm = g.d0[0] + cu * g.u[0] + cv * g.v[0];
+    const double pp = g.d0[1] + cu * g.u[1] + cv * g.v[1];
+    const double pq = g.d0[2] + cu * g.u[2] + cv * g.v[2];
+    const double dir_m = cone ? pm - g.o[0] : g.o[0], dir_p = cone ? pp - g.o[1] : g.o[1],
+                 dir_q = cone ? pq - g.o[2] : g.o[2];
+    const double org_m = cone ? g.o[0] : pm, org_p = cone ? g.o[1] : pp, org_q = cone ? g.o[2] : pq;
+    const double a_p = dir_p / dir_m, a_q = dir_q / dir_m;
+    return {a_p, org_p - a_p * org_m + 0.5 * n_p - 0.5, a_q, org_q - a_q * org_m + 0.5 * n_q - 0.5};
+}
+
+// Box (columns, rows) needed by the angle set {a, b} (b < 0: only a) over sampled tiles and slices.
+static void fp_pair_need(const tsp_projector *pr, int a, int b, int n_m, int n_p, int n_q, int &need_w, int &need_h)
+{
+    const tsp_geometry &g = pr->g;
+    const bool cone = g.kind == TSP_KIND_CONE_VEC;
+    const int tu = (g.det_cols + FPT_TU - 1) / FPT_TU, tv = (g.det_rows + FPT_TV - 1) / FPT_TV;
+    const int ut[3] = {0, tu / 2, tu - 1}, vt[3] = {0, tv / 2, tv - 1};
+    const double t0 = 0.5 - 0.5 * n_m;
+    const int kstep = std::max(1, n_m / 48);
+    need_w = need_h = 0;
+    for (int iu = 0; iu < 3; ++iu)
+        for (int iv = 0; iv < 3; ++iv) {
+            const int u0 = ut[iu] * FPT_TU, v0 = vt[iv] * FPT_TV;
+            const int u1 = std::min(u0 + FPT_TU, g.det_cols) - 1, v1 = std::min(v0 + FPT_TV, g.det_rows) - 1;
+            HostRay c[8];
+            int nc = 0;
+            for (int slot = 0; slot < (b >= 0 ? 2 : 1); ++slot)
+                for (int k = 0; k < 4; ++k)
+                    c[nc++] = host_ray(cone, pr->fp_angles[slot ? b : a], ((k & 1) ? u1 : u0) + 0.5,
+                                       ((k & 2) ? v1 : v0) + 0.5, n_p, n_q);
+            for (int k = 0; k < n_m; k += kstep) {
+                const double t = std::min(k, n_m - 1) + t0;
+                double pmin = 1e300, pmax = -1e300, qmin = 1e300, qmax = -1e300;
+                for (int i = 0; i < nc; ++i) {
+                    const double p = c[i].ap * t + c[i].cp, q = c[i].aq * t + c[i].cq;
+                    pmin = std::min(pmin, p); pmax = std::max(pmax, p);
+                    qmin = std::min(qmin, q); qmax = std::max(qmax, q);
+                }
+                if (!(pmax > -1.0 && pmin < n_p && qmax > -1.0 && qmin < n_q)) continue;  // slice not touched
+                if (!(std::isfinite(pmin) && std::isfinite(pmax) && std::isfinite(qmin) && std::isfinite(qmax))) continue;
+                const double w = std::floor(pmax + 0.01) + 2 - std::floor(pmin - 0.01) + 3;  // +3: 16-byte alignment of the start
+                const double h = std::floor(qmax + 0.01) + 2 - std::floor(qmin - 0.01);
+                if (w < 1e6) need_w = std::max(need_w, (int)w);
+                if (h < 1e6) need_h = std::max(need_h, (int)h);
+            }
+        }
+}
+
+static void plan_fp_tma_group(const tsp_projector *pr, FPGroup &grp)
+{
+    const tsp_geometry &g = pr->g;
+    const int n[3] = {g.nx, g.ny, g.nz};
+    const int n_m = n[grp.march], n_p = n[grp.p_axis], n_q = n[grp.q_axis];
+    grp.pairs.clear();
+    grp.box_w = grp.box_h = 0;
+    int box_w = 0, box_h = 0;
+    const size_t na = grp.angles.size();
+    for (size_t i = 0; i < na;) {
+        int w1, h1;
+        fp_pair_need(pr, grp.angles[i], -1, n_m, n_p, n_q, w1, h1);
+        bool paired = false;
+        if (i + 1 < na) {
+            int w2, h2;
+            fp_pair_need(pr, grp.angles[i], grp.angles[i + 1], n_m, n_p, n_q, w2, h2);
+            // pair only when sharing the box is a clear win: union at most ~25 % larger than one footprint
+            if ((double)w2 * h2 <= 1.25 * (double)w1 * h1 + 64.0) {
+                grp.pairs.push_back(grp.angles[i]);
+                grp.pairs.push_back(grp.angles[i + 1]);
+                box_w = std::max(box_w, w2); box_h = std::max(box_h, h2);
+                i += 2;
+                paired = true;
+            }
+        }
+        if (!paired) {
+            grp.pairs.push_back(grp.angles[i]);
+            grp.pairs.push_back(-1);
+            box_w = std::max(box_w, w1); box_h = std::max(box_h, h1);
+            i += 1;
+        }
+    }
+    box_w = (box_w + 1 + 3) / 4 * 4;  // one spare column; TMA boxes are whole 16-byte units
+    box_h = box_h + 1;
+    if (box_w < 8) box_w = 8;
+    if (box_w > 256 || box_h > 256) return;                 // TMA box limit
+    if ((size_t)box_w * box_h * 4 > 24 * 1024) return;      // keep >= 3 ring stages and 3 CTAs per SM
+    grp.box_w = box_w;
+    grp.box_h = box_h;
+}
+
 static int validate(const tsp_geometry *g)
 {
     if (!g) return fail(TSP_ERR_INVALID, "geometry is NULL");
@@ -191,6 +292,7 @@ extern "C" int tsp_projector_create(const tsp_geometry *geometry, tsp_projector 
         }
     }
     for (auto &kv : groups) pr->groups.push_back(std::move(kv.second));
+    for (FPGroup &grp : pr->groups) plan_fp_tma_group(pr, grp);
     *out = pr;
     return TSP_OK;
 }
@@ -203,6 +305,7 @@ static void free_device_state(tsp_projector *pr)
         if (cudaSetDevice(kv.first) != cudaSuccess) continue;
         cudaFree(kv.second.fp_angles);
         cudaFree(kv.second.fp_lists);
+        cudaFree(kv.second.fp_pairs);
         cudaFree(kv.second.bp_angles);
         cudaFree(kv.second.tmap_ring);
     }
@@ -231,6 +334,7 @@ extern "C" int tsp_projector_get_info(const tsp_projector *pr, tsp_projector_inf
     info->kernel_launches = pr->launches;
     info->bp_uses_tma = pr->bp_uses_tma;
     info->fp_uses_transpose = pr->fp_uses_transpose;
+    info->fp_uses_tma = pr->fp_uses_tma;
     return TSP_OK;
 }
 
@@ -277,6 +381,13 @@ static int get_device_state(tsp_projector *pr, int device, DeviceState **out)
         lists.insert(lists.end(), grp.angles.begin(), grp.angles.end());
     }
     CUDA_TRY(cudaMemcpy(st.fp_lists, lists.data(), lists.size() * sizeof(int), cudaMemcpyHostToDevice));
+    std::vector<int> pairs;
+    for (const FPGroup &grp : pr->groups) {
+        st.pair_offset.push_back(pairs.size() / 2);
+        pairs.insert(pairs.end(), grp.pairs.begin(), grp.pairs.end());
+    }
+    CUDA_TRY(cudaMalloc(&st.fp_pairs, std::max<size_t>(1, pairs.size()) * sizeof(int)));
+    CUDA_TRY(cudaMemcpy(st.fp_pairs, pairs.data(), pairs.size() * sizeof(int), cudaMemcpyHostToDevice));
     // keep freed scratch (the transposed volume copy) cached in the pool
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -284,6 +395,34 @@ static int get_device_state(tsp_projector *pr, int device, DeviceState **out)
         cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
     }
     *out = &(pr->dev[device] = st);
+    return TSP_OK;
+}
+
+
+// defined in the TMA section below
+static bool make_tensor_map_3d(const float *base, const uint64_t dims[3], const uint64_t stride_bytes[2],
+                               const uint32_t box[3], TensorMapBlob *out);
+// n consecutive descriptor slots from the per-device ring (descriptors of in-flight launches are
+// never overwritten: the ring is hundreds of launches deep)
+static TensorMapBlob *tmap_slots(DeviceState *st, unsigned n)
+{
+    if (st->tmap_next + n > DeviceState::kTmapSlots) st->tmap_next = 0;
+    TensorMapBlob *p = st->tmap_ring + st->tmap_next;
+    st->tmap_next += n;
+    return p;
+}
+
+template <bool CONE, bool COLS>
+static int launch_fp_tma_one(dim3 grid, size_t smem, cudaStream_t stream, const FPTmaArgs &A, const TensorMapBlob *tmap)
+{
+    static size_t configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && configured[dev] < smem) {
+        CUDA_TRY(cudaFuncSetAttribute(fp_tma_kernel<CONE, COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured[dev] = smem;
+    }
+    fp_tma_kernel<CONE, COLS><<<grid, FPT_THREADS, smem, stream>>>(A, tmap);
     return TSP_OK;
 }
 
@@ -297,17 +436,19 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
     bool need_t = false;
     for (const FPGroup &grp : pr->groups) need_t |= grp.transposed;
     float *vol_t = nullptr;
+    const int ny_pad = (g.ny + 3) / 4 * 4;  // row pitch of the transposed copy: whole 16-byte units (TMA stride rule)
     if (need_t) {
-        CUDA_TRY(cudaMallocAsync(&vol_t, nvox * sizeof(float), stream));
+        CUDA_TRY(cudaMallocAsync(&vol_t, (size_t)g.nz * g.nx * ny_pad * sizeof(float), stream));
         dim3 grid((g.nx + 31) / 32, (g.ny + 31) / 32, g.nz), block(32, 8);
-        transpose_xy_kernel<<<grid, block, 0, stream>>>(vol, vol_t, g.nx, g.ny);
+        transpose_xy_kernel<<<grid, block, 0, stream>>>(vol, vol_t, g.nx, g.ny, ny_pad);
         ++pr->launches;
     }
     pr->fp_uses_transpose = need_t ? 1 : 0;
+    int used_tma = 0;
 
     // element strides of x, y, z in the two layouts
     const long long stride_native[3] = {1, g.nx, (long long)g.nx * g.ny};
-    const long long stride_transp[3] = {g.ny, 1, (long long)g.nx * g.ny};
+    const long long stride_transp[3] = {ny_pad, 1, (long long)g.nx * ny_pad};
     for (size_t gi = 0; gi < pr->groups.size(); ++gi) {
         const FPGroup &grp = pr->groups[gi];
         const long long *stride = grp.transposed ? stride_transp : stride_native;
@@ -327,9 +468,45 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
         const double rq = pr->sigma[grp.q_axis] / pr->sigma[grp.march];
         P.rp2 = (float)(rp * rp);
         P.rq2 = (float)(rq * rq);
-        P.offsets_fit_32bit = nvox < (1ull << 31) ? 1 : 0;
+        P.offsets_fit_32bit = (size_t)g.nz * g.nx * std::max(g.ny, ny_pad) < (1ull << 31) ? 1 : 0;
         const bool cone = g.kind == TSP_KIND_CONE_VEC;
         const bool ss = g.detector_supersampling > 1;
+        // ---- TMA-staged kernel (default): needs a 16-byte aligned base and row pitch
+        if (!ss && grp.box_w > 0 && !getenv("TSP_FP_NO_TMA") && grp.pairs.size() / 2 <= 65535) {
+            const int n_second = grp.transposed ? g.nx : g.ny;  // layout dims: (p, second, nz)
+            const int pitch_p = grp.transposed ? ny_pad : g.nx;
+            const bool middle = grp.march != 2;                // marching along the middle layout axis?
+            const uint64_t dims[3] = {(uint64_t)P.n_p, (uint64_t)n_second, (uint64_t)g.nz};
+            const uint64_t strides[2] = {(uint64_t)pitch_p * 4, (uint64_t)pitch_p * 4 * (uint64_t)n_second};
+            const uint32_t box[3] = {(uint32_t)grp.box_w, middle ? 1u : (uint32_t)grp.box_h, middle ? (uint32_t)grp.box_h : 1u};
+            TensorMapBlob tmap;
+            if (make_tensor_map_3d(P.vol, dims, strides, box, &tmap)) {
+                TensorMapBlob *slot = tmap_slots(st, 1);
+                CUDA_TRY(cudaMemcpyAsync(slot, &tmap, sizeof tmap, cudaMemcpyHostToDevice, stream));
+                FPTmaArgs T;
+                T.a = P;
+                T.pairs = st->fp_pairs + 2 * st->pair_offset[gi];
+                T.box_w = grp.box_w; T.box_h = grp.box_h;
+                T.march_is_middle = middle ? 1 : 0;
+                T.stage_bytes = ((uint32_t)grp.box_w * grp.box_h * 4u + 127u) / 128u * 128u;
+                int stages = (int)((72u * 1024u) / (T.stage_bytes + 24u));
+                if (const char *e = getenv("TSP_FP_STAGES")) stages = atoi(e);
+                T.stages = std::max(2, std::min(stages, 12));
+                T.magic_off = 0u - 4u * 0x4B400000u * (uint32_t)(grp.box_w + 1);
+                const size_t smem = 128 + (size_t)T.stages * (T.stage_bytes + 24) + 16;
+                dim3 tgrid((g.det_cols + FPT_TU - 1) / FPT_TU, (unsigned)(grp.pairs.size() / 2),
+                           (g.det_rows + FPT_TV - 1) / FPT_TV);
+                int rc;
+                if (cone) rc = grp.columns ? launch_fp_tma_one<true, true>(tgrid, smem, stream, T, slot)
+                                           : launch_fp_tma_one<true, false>(tgrid, smem, stream, T, slot);
+                else rc = grp.columns ? launch_fp_tma_one<false, true>(tgrid, smem, stream, T, slot)
+                                      : launch_fp_tma_one<false, false>(tgrid, smem, stream, T, slot);
+                if (rc) return rc;
+                ++pr->launches;
+                used_tma = 1;
+                continue;
+            }
+        }
         // gridDim.y is limited to 65535: chunk the angle list
         for (size_t off = 0; off < grp.angles.size(); off += 65535) {
             const int na = (int)std::min<size_t>(65535, grp.angles.size() - off);
@@ -352,23 +529,32 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
             ++pr->launches;
         }
     }
+    pr->fp_uses_tma = used_tma;
     if (vol_t) CUDA_TRY(cudaFreeAsync(vol_t, stream));
     CUDA_TRY(cudaGetLastError());
     return TSP_OK;
 }
 
-// z voxels per thread: long register runs amortise per-angle set-up and footprint staging;
-// thin volumes (slabs, cfg 5) use short runs.  TSP_BP_ZPT overrides (tuning aid).
-static int bp_zpt_choice(int nz)
+// z voxels per thread: long register runs amortise per-angle set-up and footprint staging
+// (cfg 3: 32 -> 61.0 ms, 16 -> 69.8 ms); thin or small volumes use short runs.  TSP_BP_ZPT
+// overrides (tuning aid).
+static int bp_zpt_choice(int nx, int ny, int nz)
 {
     if (const char *e = getenv("TSP_BP_ZPT")) {
         const int v = atoi(e);
-        if (v == 1 || v == 4 || v == 8 || v == 16) return v;
+        if (v == 1 || v == 4 || v == 8 || v == 16 || v == 32) return v;
     }
-    if (nz >= 12) return 16;
-    if (nz > 4) return 8;
-    if (nz > 1) return 4;
-    return 1;
+    // longest run that (a) is not mostly padding and (b) still leaves >= 4 CTAs per SM to balance
+    const int cand[5] = {32, 16, 8, 4, 1};
+    const long long tiles_xy = (long long)((nx + BP_TX - 1) / BP_TX) * ((ny + BP_TY - 1) / BP_TY);
+    int fallback = 1;
+    for (int i = 0; i < 5; ++i) {
+        const int z = cand[i];
+        if (z > 1 && nz < (3 * z) / 4) continue;  // run mostly outside the volume
+        if (fallback == 1) fallback = z;
+        if (tiles_xy * ((nz + z - 1) / z) >= 4LL * 148) return z;
+    }
+    return std::min(fallback, 8);
 }
 
 template <bool CONE, int ZPT>
@@ -397,6 +583,7 @@ static int launch_bp_variant(bool cone, int zpt, dim3 grid, dim3 block, cudaStre
         TSP_BP_CASE(4)
         TSP_BP_CASE(8)
         TSP_BP_CASE(16)
+        TSP_BP_CASE(32)
     }
 #undef TSP_BP_CASE
     return fail(TSP_ERR_INVALID, "unsupported z run %d", zpt);
@@ -425,22 +612,34 @@ static PFN_tensorMapEncodeTiled tensor_map_encoder()
     return fn;
 }
 
-// Tensor map over the projection stack viewed as (u, angle, v), box = 64 x 1 x rows.
-static bool make_proj_tensor_map(const float *proj, int det_u, int n_angles, int det_v, int box_rows, TensorMapBlob *out)
+static bool make_tensor_map_3d(const float *base, const uint64_t dims[3], const uint64_t stride_bytes[2],
+                               const uint32_t box[3], TensorMapBlob *out)
 {
     static_assert(sizeof(CUtensorMap) == sizeof(TensorMapBlob), "CUtensorMap is 128 bytes");
     PFN_tensorMapEncodeTiled enc = tensor_map_encoder();
     if (!enc) return false;
-    if ((reinterpret_cast<uintptr_t>(proj) & 15u) != 0 || (det_u & 3) != 0) return false;
-    const cuuint64_t dims[3] = {(cuuint64_t)det_u, (cuuint64_t)n_angles, (cuuint64_t)det_v};
-    const cuuint64_t strides[2] = {(cuuint64_t)det_u * 4, (cuuint64_t)det_u * 4 * (cuuint64_t)n_angles};
-    const cuuint32_t box[3] = {(cuuint32_t)BP_TMA_PITCH, 1u, (cuuint32_t)box_rows};
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) != 0) return false;
+    if ((stride_bytes[0] & 15u) != 0 || (stride_bytes[1] & 15u) != 0) return false;
+    if (stride_bytes[0] >= (1ull << 40) || stride_bytes[1] >= (1ull << 40)) return false;
+    if (box[0] > 256 || box[1] > 256 || box[2] > 256 || (box[0] & 3u) != 0) return false;
+    const cuuint64_t d[3] = {dims[0], dims[1], dims[2]};
+    const cuuint64_t st[2] = {stride_bytes[0], stride_bytes[1]};
+    const cuuint32_t bx[3] = {box[0], box[1], box[2]};
     const cuuint32_t estr[3] = {1u, 1u, 1u};
-    if (strides[1] >= (1ull << 40)) return false;
-    CUresult r = enc(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(proj),
-                     dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+    CUresult r = enc(reinterpret_cast<CUtensorMap *>(out), CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float *>(base),
+                     d, st, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS;
+}
+
+// Tensor map over the projection stack viewed as (u, angle, v), box = cols x 1 x rows.
+static bool make_proj_tensor_map(const float *proj, int det_u, int n_angles, int det_v, int box_cols, int box_rows,
+                                 TensorMapBlob *out)
+{
+    const uint64_t dims[3] = {(uint64_t)det_u, (uint64_t)n_angles, (uint64_t)det_v};
+    const uint64_t strides[2] = {(uint64_t)det_u * 4, (uint64_t)det_u * 4 * (uint64_t)n_angles};
+    const uint32_t box[3] = {(uint32_t)box_cols, 1u, (uint32_t)box_rows};
+    return make_tensor_map_3d(proj, dims, strides, box, out);
 }
 
 template <bool CONE, int ZPT>
@@ -470,6 +669,7 @@ static int launch_bp_tma_variant(bool cone, int zpt, dim3 grid, cudaStream_t str
         TSP_BP_CASE(4)
         TSP_BP_CASE(8)
         TSP_BP_CASE(16)
+        TSP_BP_CASE(32)
     }
 #undef TSP_BP_CASE
     return fail(TSP_ERR_INVALID, "unsupported z run %d", zpt);
@@ -487,6 +687,8 @@ static int launch_bp(tsp_projector *pr, DeviceState *st, float *vol, const float
     P.out_scale = (float)(pr->sigma[0] * pr->sigma[1] * pr->sigma[2]);
     P.additive = additive;
     P.vox_ss = g.voxel_supersampling;
+    P.magic_off = 0;
+    P.magic_off_b = 0;
     const bool cone = g.kind == TSP_KIND_CONE_VEC;
     int used_tma = 0;
     if (g.voxel_supersampling > 1) {
@@ -495,19 +697,22 @@ static int launch_bp(tsp_projector *pr, DeviceState *st, float *vol, const float
         if (cone) bp_supersample_kernel<true><<<grid, block, 0, stream>>>(P);
         else bp_supersample_kernel<false><<<grid, block, 0, stream>>>(P);
     } else {
-        const int zpt = bp_zpt_choice(g.nz);
+        const int zpt = bp_zpt_choice(g.nx, g.ny, g.nz);
         const int gz = (g.nz + zpt - 1) / zpt;
         const int gy = (g.ny + BP_TY - 1) / BP_TY;
         if (gz > 65535 || gy > 65535) return fail(TSP_ERR_INVALID, "volume too large for the BP grid");
         dim3 grid((g.nx + BP_TX - 1) / BP_TX, gy, gz), block(BP_TX, BP_TY);
-        TensorMapBlob tmap;
+        TensorMapBlob tmap[2];
         const bool use_tma = !getenv("TSP_BP_NO_TMA") &&
-                             make_proj_tensor_map(proj, g.det_cols, g.n_angles, g.det_rows, bp_wv(zpt), &tmap);
+                             make_proj_tensor_map(proj, g.det_cols, g.n_angles, g.det_rows, BP_TMA_PITCH, bp_wv(zpt), &tmap[0]) &&
+                             make_proj_tensor_map(proj, g.det_cols, g.n_angles, g.det_rows, BP_TMA_PITCH_B, bp_wv(zpt), &tmap[1]);
+        P.magic_off = 0u - 4u * BP_MAGIC_BITS * (uint32_t)((use_tma ? BP_TMA_PITCH : BP_PITCH) + 1);
+        P.magic_off_b = 0u - 4u * BP_MAGIC_BITS * (uint32_t)(BP_TMA_PITCH_B + 1);
         if (use_tma) {
             // The descriptor lives in device memory (a small ring per device, so that
             // back-to-back asynchronous calls never overwrite a descriptor in use).
-            TensorMapBlob *slot = st->tmap_ring + (st->tmap_next++ % DeviceState::kTmapSlots);
-            CUDA_TRY(cudaMemcpyAsync(slot, &tmap, sizeof tmap, cudaMemcpyHostToDevice, stream));
+            TensorMapBlob *slot = tmap_slots(st, 2);
+            CUDA_TRY(cudaMemcpyAsync(slot, tmap, sizeof tmap, cudaMemcpyHostToDevice, stream));
             if (int rc = launch_bp_tma_variant(cone, zpt, grid, stream, P, slot)) return rc;
         } else {
             if (int rc = launch_bp_variant(cone, zpt, grid, block, stream, P)) return rc;
