@@ -1,0 +1,8 @@
+set -x
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+TSP_DEBUG=1 python scratch/prof_step.py 512 720 3 2>&1 | tail -8
+TSP_FP_ONE_PITCH=1 python scratch/prof_step.py 512 720 2 2>&1 | tail -2
+python scratch/prof_step.py 512 720 2 par 2>&1 | tail -2
+python scratch/prof_step.py 256 180 3 par 2>&1 | tail -2
+python scratch/prof_step.py 1024 360 2 2>&1 | tail -2
+ncu --set full --clock-control none --import-source on -k regex:'fp_tma' -c 1 -o gpurun_out/prof_fp_v6 python scratch/prof_step.py 512 720 1 > gpurun_out/prof_fp_v6.log 2>&1

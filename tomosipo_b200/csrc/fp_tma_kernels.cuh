@@ -9,7 +9,7 @@
 //     the TMA engine copy that box of the slice into a shared-memory ring stage;
 //     voxels outside the volume arrive as zeros, which is the projector's border
 //     rule - so there is no bounds-checked "careful" loop at all;
-//   * the 8 consumer warps (4 per angle, 4 detector rows per thread) take their
+//   * the 8 consumer warps (16 columns x 2 angles per warp, 4 detector rows per thread) take their
 //     four bilinear taps from shared memory (bank-granular, not line-granular
 //     like the L1 path: ncu showed the LDG kernel bound by L1 wavefronts, ~2
 //     128-byte lines per tap instruction);
@@ -25,19 +25,24 @@
 namespace tsp {
 
 constexpr int FPT_TU = 32;         // det_u pixels per CTA
-constexpr int FPT_R = 4;           // det_v rows per thread
-constexpr int FPT_TV = 4 * FPT_R;  // det_v rows per CTA (4 warps per angle)
+// det_v rows per thread: template parameter R (4 or 8); a CTA covers 4 * R rows
+__host__ __device__ constexpr int fpt_min_ctas(int r) { return r >= 8 ? 2 : 3; }
 constexpr int FPT_CONSUMERS = 256;
 constexpr int FPT_THREADS = FPT_CONSUMERS + 32;
 
 struct FPTmaArgs {
     FPArgs a;               // volume (for the fallback path), dims, angle table, list, output
     const int *pairs;       // angle pairs of this launch: {a, b} with b = -1 for a single angle
-    int box_w, box_h;       // staged box, elements (box_w % 4 == 0)
+    // Two staged-box variants that differ in row pitch (= box width): a warp's lanes sit on a few
+    // neighbouring rows of the box; which pitch residue (mod 32 banks) keeps them on distinct
+    // banks depends on whether column and row move together along the lanes
+    // (scratch/bank_sim_fp2.py).  The producer picks the variant per CTA; tmap[v] has box_w[v].
+    int box_w[2];           // elements, multiples of 4
+    int box_h;
+    uint32_t magic_off[2];  // -4 * MAGIC_BITS * (box_w + 1) mod 2^32 (run-time on purpose, see BPArgs)
     int march_is_middle;    // tensor coordinates are (p, k, q) if set, (p, q, k) otherwise
     int stages;
-    uint32_t stage_bytes;   // box_w * box_h * 4 rounded up to 128
-    uint32_t magic_off;     // -4 * MAGIC_BITS * (box_w + 1) mod 2^32 (run-time on purpose, see BPArgs)
+    uint32_t stage_bytes;   // max box bytes rounded up to 128
 };
 
 struct FPRay {
@@ -97,10 +102,68 @@ __device__ __forceinline__ void fpt_slice_box(const FPRay (&c)[8], float t, floa
     pmin -= 0.01f; qmin -= 0.01f; pmax += 0.01f; qmax += 0.01f;
 }
 
-template <bool CONE, bool COLS>
-__global__ void __launch_bounds__(FPT_THREADS, 3) fp_tma_kernel(const FPTmaArgs A, const TensorMapBlob *__restrict__ tmap)
+// Consumer march over the hull slices [kA, kD) for pitch variant V (box_w[V] stays in a
+// uniform register, so the second tap row is addressed as [a0 + UR]).
+template <bool COLS, int V, int R>
+__device__ __forceinline__ void fpt_consume(const FPTmaArgs &A, int kA, int kD, float t0, uint32_t ctrl, uint32_t full,
+                                            uint32_t empty, int lane, const float *ap, const float *cp,
+                                            const float (&aq)[R], const float (&cq)[R], float (&acc)[R])
 {
-    constexpr int R = FPT_R;
+    const FPArgs &P = A.a;
+    const float MAGIC = 12582912.0f;
+    const uint32_t bw4 = (uint32_t)A.box_w[V] * 4u;
+    float t = (float)kA + t0;
+    int s = 0;
+    uint32_t parity = 0u;
+    for (int k = kA; k < kD; ++k) {
+        mbar_wait(full + 8u * s, parity);
+        uint32_t sb, fit;
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(sb), "=r"(fit) : "r"(ctrl + 8u * s) : "memory");
+        if (fit) {
+            float wp = 0.0f;
+            uint32_t offp = 0u;
+            if (COLS) {
+                const float fp = fmaf(ap[0], t, cp[0]);
+                const float rp = __fadd_rd(fp, MAGIC);
+                wp = fp - (rp - MAGIC);
+                offp = __float_as_uint(rp) * 4u + sb;
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                if (!COLS) {
+                    const float fp = fmaf(ap[COLS ? 0 : r], t, cp[COLS ? 0 : r]);
+                    const float rp = __fadd_rd(fp, MAGIC);
+                    wp = fp - (rp - MAGIC);
+                    offp = __float_as_uint(rp) * 4u + sb;
+                }
+                const float fq = fmaf(aq[r], t, cq[r]);
+                const float rq = __fadd_rd(fq, MAGIC);
+                const float wq = fq - (rq - MAGIC);
+                const uint32_t a0 = __float_as_uint(rq) * bw4 + offp;
+                const uint32_t a1 = a0 + bw4;
+                const float v00 = fpt_lds<0>(a0), v10 = fpt_lds<4>(a0);
+                const float v01 = fpt_lds<0>(a1), v11 = fpt_lds<4>(a1);
+                const float lo = fmaf(wp, v10 - v00, v00);
+                const float hi = fmaf(wp, v11 - v01, v01);
+                acc[r] += fmaf(wq, hi - lo, lo);
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+                careful_range(P, ap[COLS ? 0 : r], aq[r], cp[COLS ? 0 : r], cq[r], t0, k, k + 1, acc[r]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(empty + 8u * s);
+        if (++s == A.stages) { s = 0; parity ^= 1u; }
+        t += 1.0f;
+    }
+}
+
+template <bool CONE, bool COLS, int R>
+__global__ void __launch_bounds__(FPT_THREADS, fpt_min_ctas(R))
+fp_tma_kernel(const FPTmaArgs A, const TensorMapBlob *__restrict__ tmap)
+{
+    constexpr int FPT_TV = 4 * R;
     const FPArgs &P = A.a;
     extern __shared__ __align__(128) unsigned char fpt_smem[];
     unsigned char *base = fpt_smem + ((128u - (smem_u32(fpt_smem) & 127u)) & 127u);
@@ -108,7 +171,7 @@ __global__ void __launch_bounds__(FPT_THREADS, 3) fp_tma_kernel(const FPTmaArgs 
     const uint32_t ctrl = bufs + (uint32_t)A.stages * A.stage_bytes;  // per stage: {uint32 sb, uint32 fit}
     const uint32_t full = ctrl + 8u * A.stages;
     const uint32_t empty = full + 8u * A.stages;
-    int *hull = reinterpret_cast<int *>(base + (size_t)A.stages * (A.stage_bytes + 24u));  // {kA, kD}
+    int *hull = reinterpret_cast<int *>(base + (size_t)A.stages * (A.stage_bytes + 24u));  // {kA, kD, variant}
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int pair_a = A.pairs[2 * blockIdx.y], pair_b = A.pairs[2 * blockIdx.y + 1];
@@ -160,12 +223,25 @@ __global__ void __launch_bounds__(FPT_THREADS, 3) fp_tma_kernel(const FPTmaArgs 
             }
         }
         if (kD <= kA) { kA = 0; kD = 0; }
-        if (lane == 0) { hull[0] = kA; hull[1] = kD; }
+        // pitch variant: do column and row move together along u (at the middle of the hull)?
+        int variant = 0;
+        {
+            const float tm = 0.5f * (float)(kA + kD) + t0;
+            const float dp = (fmaf(c[1].ap, tm, c[1].cp) + fmaf(c[3].ap, tm, c[3].cp)) -
+                             (fmaf(c[0].ap, tm, c[0].cp) + fmaf(c[2].ap, tm, c[2].cp));
+            const float dq = (fmaf(c[1].aq, tm, c[1].cq) + fmaf(c[3].aq, tm, c[3].cq)) -
+                             (fmaf(c[0].aq, tm, c[0].cq) + fmaf(c[2].aq, tm, c[2].cq));
+            variant = (dp * dq < 0.0f) ? 1 : 0;
+        }
+        if (lane == 0) { hull[0] = kA; hull[1] = kD; hull[2] = variant; }
         __syncthreads();
 
         int s = 0;
         uint32_t parity = 1u;
-        const uint32_t box_bytes = (uint32_t)A.box_w * (uint32_t)A.box_h * 4u;
+        const int bw = A.box_w[variant];
+        const uint32_t moff = A.magic_off[variant];
+        const uint32_t box_bytes = (uint32_t)bw * (uint32_t)A.box_h * 4u;
+        const TensorMapBlob *tm = tmap + variant;
         for (int k0 = kA; k0 < kD; k0 += 32) {
             const int k = k0 + lane;
             float pmin, pmax, qmin, qmax;
@@ -176,7 +252,7 @@ __global__ void __launch_bounds__(FPT_THREADS, 3) fp_tma_kernel(const FPTmaArgs 
             int p0 = __float2int_rd(pmin);
             p0 -= ((p0 % 4) + 4) % 4;  // TMA: innermost coordinate on a 16-byte boundary
             const int q0 = __float2int_rd(qmin);
-            const int fit = (__float2int_rd(pmax) + 2 - p0 <= A.box_w) && (__float2int_rd(qmax) + 2 - q0 <= A.box_h) &&
+            const int fit = (__float2int_rd(pmax) + 2 - p0 <= bw) && (__float2int_rd(qmax) + 2 - q0 <= A.box_h) &&
                             (pmax >= pmin) && (qmax >= qmin);
             const int nj = min(32, kD - k0);
             for (int j = 0; j < nj; ++j) {
@@ -186,13 +262,13 @@ __global__ void __launch_bounds__(FPT_THREADS, 3) fp_tma_kernel(const FPTmaArgs 
                 mbar_wait(empty + 8u * s, parity);
                 if (lane == 0) {
                     const uint32_t dst = bufs + (uint32_t)s * A.stage_bytes;
-                    const uint32_t sb = dst - 4u * (uint32_t)(q0j * A.box_w + p0j) + A.magic_off;
+                    const uint32_t sb = dst - 4u * (uint32_t)(q0j * bw + p0j) + moff;
                     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ctrl + 8u * s), "r"(sb), "r"((uint32_t)fitj)
                                  : "memory");
                     if (fitj) {
                         mbar_arrive_expect_tx(full + 8u * s, box_bytes);
-                        if (A.march_is_middle) fpt_tma_box(dst, tmap, p0j, k0 + j, q0j, full + 8u * s);
-                        else fpt_tma_box(dst, tmap, p0j, q0j, k0 + j, full + 8u * s);
+                        if (A.march_is_middle) fpt_tma_box(dst, tm, p0j, k0 + j, q0j, full + 8u * s);
+                        else fpt_tma_box(dst, tm, p0j, q0j, k0 + j, full + 8u * s);
                     } else {
                         mbar_arrive(full + 8u * s);
                     }
@@ -205,12 +281,15 @@ __global__ void __launch_bounds__(FPT_THREADS, 3) fp_tma_kernel(const FPTmaArgs 
     }
 
     // --------------------------------------------------------------- consumers
-    const int slot = warp >> 2;                 // which angle of the pair
+    // A warp = 16 detector columns x the 2 angles of the pair (lanes 0-15 / 16-31): the two
+    // half-warps sample nearly the same voxels, so a tap instruction touches <= ~32 distinct
+    // words (32 consecutive columns of one angle span 40-60 words: always >= 2 wavefronts).
+    const int slot = lane >> 4;
     const bool slot_live = slot < n_in_pair;
-    const int a = slot_live && slot ? pair_b : pair_a;
+    const int a = (slot_live && slot) ? pair_b : pair_a;
     const FPAngle g = P.angles[a];
-    const int iu = u0 + lane;
-    const int iv0 = v0 + (warp & 3) * R;
+    const int iu = u0 + (warp & 1) * 16 + (lane & 15);
+    const int iv0 = v0 + (warp >> 1) * R;
     // out-of-detector lanes / rows shadow the tile's last pixel: their taps stay inside the staged box
     const double cu = (double)min(iu, u1) + 0.5;
 
@@ -224,55 +303,9 @@ __global__ void __launch_bounds__(FPT_THREADS, 3) fp_tma_kernel(const FPTmaArgs 
         acc[r] = 0.0f;
     }
     __syncthreads();
-    const int kA = hull[0], kD = hull[1];
-
-    const float MAGIC = 12582912.0f;
-    const uint32_t bw4 = (uint32_t)A.box_w * 4u;
-    float t = (float)kA + t0;
-    int s = 0;
-    uint32_t parity = 0u;
-    for (int k = kA; k < kD; ++k) {
-        mbar_wait(full + 8u * s, parity);
-        uint32_t sb, fit;
-        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(sb), "=r"(fit) : "r"(ctrl + 8u * s) : "memory");
-        if (fit) {
-            float wp = 0.0f;
-            uint32_t offp = 0u;
-            if (COLS) {
-                const float fp = fmaf(ap[0], t, cp[0]);
-                const float rp = __fadd_rd(fp, MAGIC);
-                wp = fp - (rp - MAGIC);
-                offp = __float_as_uint(rp) * 4u + sb;
-            }
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                if (!COLS) {
-                    const float fp = fmaf(ap[COLS ? 0 : r], t, cp[COLS ? 0 : r]);
-                    const float rp = __fadd_rd(fp, MAGIC);
-                    wp = fp - (rp - MAGIC);
-                    offp = __float_as_uint(rp) * 4u + sb;
-                }
-                const float fq = fmaf(aq[r], t, cq[r]);
-                const float rq = __fadd_rd(fq, MAGIC);
-                const float wq = fq - (rq - MAGIC);
-                const uint32_t a0 = __float_as_uint(rq) * bw4 + offp;
-                const uint32_t a1 = a0 + bw4;
-                const float v00 = fpt_lds<0>(a0), v10 = fpt_lds<4>(a0);
-                const float v01 = fpt_lds<0>(a1), v11 = fpt_lds<4>(a1);
-                const float lo = fmaf(wp, v10 - v00, v00);
-                const float hi = fmaf(wp, v11 - v01, v01);
-                acc[r] += fmaf(wq, hi - lo, lo);
-            }
-        } else {
-#pragma unroll
-            for (int r = 0; r < R; ++r)
-                careful_range(P, ap[COLS ? 0 : r], aq[r], cp[COLS ? 0 : r], cq[r], t0, k, k + 1, acc[r]);
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(empty + 8u * s);
-        if (++s == A.stages) { s = 0; parity ^= 1u; }
-        t += 1.0f;
-    }
+    const int kA = hull[0], kD = hull[1], variant = hull[2];
+    if (variant) fpt_consume<COLS, 1, R>(A, kA, kD, t0, ctrl, full, empty, lane, ap, cp, aq, cq, acc);
+    else fpt_consume<COLS, 0, R>(A, kA, kD, t0, ctrl, full, empty, lane, ap, cp, aq, cq, acc);
 
     if (slot_live && iu < P.det_u) {
 #pragma unroll

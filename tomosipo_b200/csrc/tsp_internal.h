@@ -46,6 +46,7 @@ struct FPGroup {
     // coincides (second = -1: single), and the staged box that bounds every pair's footprint.
     std::vector<int> pairs;  // 2 ints per pair
     int box_w = 0, box_h = 0;  // 0: group not eligible
+    int rows_per_thread = 4;   // 4 or 8: a CTA covers 32 x (4 * rows_per_thread) pixels
 };
 
 // The tensor map is an opaque 128-byte, 64-byte aligned CUtensorMap.

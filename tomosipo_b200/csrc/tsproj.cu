@@ -139,19 +139,20 @@ static HostRay host_ray(bool cone, const FPAngle &g, double cu, double cv, int n
 }
 
 // Box (columns, rows) needed by the angle set {a, b} (b < 0: only a) over sampled tiles and slices.
-static void fp_pair_need(const tsp_projector *pr, int a, int b, int n_m, int n_p, int n_q, int &need_w, int &need_h)
+static void fp_pair_need(const tsp_projector *pr, int a, int b, int n_m, int n_p, int n_q, int tile_v, int &need_w,
+                         int &need_h)
 {
     const tsp_geometry &g = pr->g;
     const bool cone = g.kind == TSP_KIND_CONE_VEC;
-    const int tu = (g.det_cols + FPT_TU - 1) / FPT_TU, tv = (g.det_rows + FPT_TV - 1) / FPT_TV;
+    const int tu = (g.det_cols + FPT_TU - 1) / FPT_TU, tv = (g.det_rows + tile_v - 1) / tile_v;
     const int ut[3] = {0, tu / 2, tu - 1}, vt[3] = {0, tv / 2, tv - 1};
     const double t0 = 0.5 - 0.5 * n_m;
     const int kstep = std::max(1, n_m / 48);
     need_w = need_h = 0;
     for (int iu = 0; iu < 3; ++iu)
         for (int iv = 0; iv < 3; ++iv) {
-            const int u0 = ut[iu] * FPT_TU, v0 = vt[iv] * FPT_TV;
-            const int u1 = std::min(u0 + FPT_TU, g.det_cols) - 1, v1 = std::min(v0 + FPT_TV, g.det_rows) - 1;
+            const int u0 = ut[iu] * FPT_TU, v0 = vt[iv] * tile_v;
+            const int u1 = std::min(u0 + FPT_TU, g.det_cols) - 1, v1 = std::min(v0 + tile_v, g.det_rows) - 1;
             HostRay c[8];
             int nc = 0;
             for (int slot = 0; slot < (b >= 0 ? 2 : 1); ++slot)
@@ -168,8 +169,11 @@ static void fp_pair_need(const tsp_projector *pr, int a, int b, int n_m, int n_p
                 }
                 if (!(pmax > -1.0 && pmin < n_p && qmax > -1.0 && qmin < n_q)) continue;  // slice not touched
                 if (!(std::isfinite(pmin) && std::isfinite(pmax) && std::isfinite(qmin) && std::isfinite(qmax))) continue;
-                const double w = std::floor(pmax + 0.01) + 2 - std::floor(pmin - 0.01) + 3;  // +3: 16-byte alignment of the start
-                const double h = std::floor(qmax + 0.01) + 2 - std::floor(qmin - 0.01);
+                // columns floor(pmin) .. floor(pmax) + 1 at the worst phase of pmin on the voxel grid,
+                // + 3 for aligning the start down to 16 bytes; spans vary smoothly between the
+                // sampled tiles / slices: 2 % + 0.05 slack
+                const double w = std::floor(1.02 * (pmax - pmin) + 0.07) + 3 + 3;
+                const double h = std::floor(1.02 * (qmax - qmin) + 0.07) + 3;
                 if (w < 1e6) need_w = std::max(need_w, (int)w);
                 if (h < 1e6) need_h = std::max(need_h, (int)h);
             }
@@ -183,15 +187,20 @@ static void plan_fp_tma_group(const tsp_projector *pr, FPGroup &grp)
     const int n_m = n[grp.march], n_p = n[grp.p_axis], n_q = n[grp.q_axis];
     grp.pairs.clear();
     grp.box_w = grp.box_h = 0;
+    // rows per thread: 8 amortises the per-slice synchronisation over twice the samples; small
+    // detectors keep 4 so that the grid still fills the GPU.  TSP_FP_R overrides (tuning aid).
+    grp.rows_per_thread = (g.det_rows >= 128 && (long long)g.det_rows * g.det_cols >= 256LL * 256) ? 8 : 4;
+    if (const char *e = getenv("TSP_FP_R")) grp.rows_per_thread = atoi(e) == 8 ? 8 : 4;
+    const int tile_v = 4 * grp.rows_per_thread;
     int box_w = 0, box_h = 0;
     const size_t na = grp.angles.size();
     for (size_t i = 0; i < na;) {
         int w1, h1;
-        fp_pair_need(pr, grp.angles[i], -1, n_m, n_p, n_q, w1, h1);
+        fp_pair_need(pr, grp.angles[i], -1, n_m, n_p, n_q, tile_v, w1, h1);
         bool paired = false;
         if (i + 1 < na) {
             int w2, h2;
-            fp_pair_need(pr, grp.angles[i], grp.angles[i + 1], n_m, n_p, n_q, w2, h2);
+            fp_pair_need(pr, grp.angles[i], grp.angles[i + 1], n_m, n_p, n_q, tile_v, w2, h2);
             // pair only when sharing the box is a clear win: union at most ~25 % larger than one footprint
             if ((double)w2 * h2 <= 1.25 * (double)w1 * h1 + 64.0) {
                 grp.pairs.push_back(grp.angles[i]);
@@ -208,11 +217,10 @@ static void plan_fp_tma_group(const tsp_projector *pr, FPGroup &grp)
             i += 1;
         }
     }
-    box_w = (box_w + 1 + 3) / 4 * 4;  // one spare column; TMA boxes are whole 16-byte units
-    box_h = box_h + 1;
+    box_w = (box_w + 3) / 4 * 4;  // TMA boxes are whole 16-byte units
     if (box_w < 8) box_w = 8;
     if (box_w > 256 || box_h > 256) return;                 // TMA box limit
-    if ((size_t)box_w * box_h * 4 > 24 * 1024) return;      // keep >= 3 ring stages and 3 CTAs per SM
+    if ((size_t)box_w * box_h * 4 > 32 * 1024) return;      // keep >= 3 ring stages
     grp.box_w = box_w;
     grp.box_h = box_h;
 }
@@ -412,17 +420,17 @@ static TensorMapBlob *tmap_slots(DeviceState *st, unsigned n)
     return p;
 }
 
-template <bool CONE, bool COLS>
+template <bool CONE, bool COLS, int R>
 static int launch_fp_tma_one(dim3 grid, size_t smem, cudaStream_t stream, const FPTmaArgs &A, const TensorMapBlob *tmap)
 {
     static size_t configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && configured[dev] < smem) {
-        CUDA_TRY(cudaFuncSetAttribute(fp_tma_kernel<CONE, COLS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(fp_tma_kernel<CONE, COLS, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[dev] = smem;
     }
-    fp_tma_kernel<CONE, COLS><<<grid, FPT_THREADS, smem, stream>>>(A, tmap);
+    fp_tma_kernel<CONE, COLS, R><<<grid, FPT_THREADS, smem, stream>>>(A, tmap);
     return TSP_OK;
 }
 
@@ -478,29 +486,55 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
             const bool middle = grp.march != 2;                // marching along the middle layout axis?
             const uint64_t dims[3] = {(uint64_t)P.n_p, (uint64_t)n_second, (uint64_t)g.nz};
             const uint64_t strides[2] = {(uint64_t)pitch_p * 4, (uint64_t)pitch_p * 4 * (uint64_t)n_second};
-            const uint32_t box[3] = {(uint32_t)grp.box_w, middle ? 1u : (uint32_t)grp.box_h, middle ? (uint32_t)grp.box_h : 1u};
-            TensorMapBlob tmap;
-            if (make_tensor_map_3d(P.vol, dims, strides, box, &tmap)) {
-                TensorMapBlob *slot = tmap_slots(st, 1);
-                CUDA_TRY(cudaMemcpyAsync(slot, &tmap, sizeof tmap, cudaMemcpyHostToDevice, stream));
+            // two pitch variants: box widths >= the needed width whose residue mod 32 banks is
+            // {4, 8} (column and row move together along a warp) or {24, 28} (opposite)
+            int bw[2] = {0, 0};
+            for (int w = grp.box_w; w <= grp.box_w + 32 && !(bw[0] && bw[1]); w += 4) {
+                const int r = w & 31;
+                if (!bw[0] && (r == 4 || r == 8)) bw[0] = w;
+                if (!bw[1] && (r == 24 || r == 28)) bw[1] = w;
+            }
+            if (getenv("TSP_FP_ONE_PITCH")) bw[0] = bw[1] = grp.box_w;
+            // a much wider box costs more L2 traffic than the conflicts it avoids
+            if (bw[0] > std::min(bw[1], grp.box_w) + 16) bw[0] = bw[1];
+            if (bw[1] > std::min(bw[0], grp.box_w) + 16) bw[1] = bw[0];
+            if (bw[0] > 256 || bw[1] > 256) bw[0] = bw[1] = grp.box_w;
+            TensorMapBlob tmap[2];
+            bool ok = true;
+            for (int v = 0; v < 2 && ok; ++v) {
+                const uint32_t box[3] = {(uint32_t)bw[v], middle ? 1u : (uint32_t)grp.box_h, middle ? (uint32_t)grp.box_h : 1u};
+                ok = make_tensor_map_3d(P.vol, dims, strides, box, &tmap[v]);
+            }
+            if (ok) {
+                TensorMapBlob *slot = tmap_slots(st, 2);
+                CUDA_TRY(cudaMemcpyAsync(slot, tmap, sizeof tmap, cudaMemcpyHostToDevice, stream));
                 FPTmaArgs T;
                 T.a = P;
                 T.pairs = st->fp_pairs + 2 * st->pair_offset[gi];
-                T.box_w = grp.box_w; T.box_h = grp.box_h;
+                T.box_h = grp.box_h;
+                for (int v = 0; v < 2; ++v) {
+                    T.box_w[v] = bw[v];
+                    T.magic_off[v] = 0u - 4u * 0x4B400000u * (uint32_t)(bw[v] + 1);
+                }
                 T.march_is_middle = middle ? 1 : 0;
-                T.stage_bytes = ((uint32_t)grp.box_w * grp.box_h * 4u + 127u) / 128u * 128u;
-                int stages = (int)((72u * 1024u) / (T.stage_bytes + 24u));
+                T.stage_bytes = ((uint32_t)std::max(bw[0], bw[1]) * grp.box_h * 4u + 127u) / 128u * 128u;
+                const int R = grp.rows_per_thread;
+                int stages = (int)(((R == 8 ? 108u : 72u) * 1024u) / (T.stage_bytes + 24u));
                 if (const char *e = getenv("TSP_FP_STAGES")) stages = atoi(e);
                 T.stages = std::max(2, std::min(stages, 12));
-                T.magic_off = 0u - 4u * 0x4B400000u * (uint32_t)(grp.box_w + 1);
+                if (getenv("TSP_DEBUG"))
+                    fprintf(stderr, "[tsp] fp group march=%d transposed=%d cols=%d R=%d: %zu pairs, box need %dx%d, pitches %d/%d, %d stages of %u B\n",
+                            grp.march, (int)grp.transposed, (int)grp.columns, R, grp.pairs.size() / 2, grp.box_w, grp.box_h,
+                            bw[0], bw[1], T.stages, T.stage_bytes);
                 const size_t smem = 128 + (size_t)T.stages * (T.stage_bytes + 24) + 16;
                 dim3 tgrid((g.det_cols + FPT_TU - 1) / FPT_TU, (unsigned)(grp.pairs.size() / 2),
-                           (g.det_rows + FPT_TV - 1) / FPT_TV);
+                           (g.det_rows + 4 * R - 1) / (4 * R));
                 int rc;
-                if (cone) rc = grp.columns ? launch_fp_tma_one<true, true>(tgrid, smem, stream, T, slot)
-                                           : launch_fp_tma_one<true, false>(tgrid, smem, stream, T, slot);
-                else rc = grp.columns ? launch_fp_tma_one<false, true>(tgrid, smem, stream, T, slot)
-                                      : launch_fp_tma_one<false, false>(tgrid, smem, stream, T, slot);
+#define TSP_FPT(C, L) (R == 8 ? launch_fp_tma_one<C, L, 8>(tgrid, smem, stream, T, slot) \
+                              : launch_fp_tma_one<C, L, 4>(tgrid, smem, stream, T, slot))
+                if (cone) rc = grp.columns ? TSP_FPT(true, true) : TSP_FPT(true, false);
+                else rc = grp.columns ? TSP_FPT(false, true) : TSP_FPT(false, false);
+#undef TSP_FPT
                 if (rc) return rc;
                 ++pr->launches;
                 used_tma = 1;
