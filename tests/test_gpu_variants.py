@@ -1,0 +1,140 @@
+"""Every kernel variant of the hot path against the fp64 oracle and against each other.
+
+The library picks its FP / BP kernels from the geometry (TMA-staged vs. plain
+loads, rows per thread, z-run length, shared-memory pitch).  Tuning
+environment variables (read by libtsproj at projector creation / launch) force
+each variant here so that all of them stay parity-green, including the
+fallback paths a default run of the large configurations never takes.
+
+Tolerance: relative L2 <= 1e-5 against the fp64 oracle (BASELINE.json
+north_star); variants among themselves differ only by fp32 summation order
+(<= 2e-6).
+"""
+import os
+from contextlib import contextmanager
+
+import numpy as np
+import pytest
+
+from oracle import oracle as O
+
+from .test_gpu_kernels import TOL, _run, cases, make, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+@contextmanager
+def env(**kw):
+    old = {k: os.environ.get(k) for k in kw}
+    os.environ.update({k: str(v) for k, v in kw.items()})
+    try:
+        yield
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+FP_VARIANTS = [
+    {},                                   # default plan
+    {"TSP_FP_NO_TMA": 1},                 # plain-load kernels (fp_cols_kernel / fp_kernel)
+    {"TSP_FP_R": 4},
+    {"TSP_FP_R": 8},
+    {"TSP_FP_ONE_PITCH": 1},
+    {"TSP_FP_BOX_SHRINK": 3},             # undersized box: some slices take the "unfit" global path
+    {"TSP_FP_BOX_SHRINK": 40},            # box far too small: every slice unfit
+    {"TSP_FP_STAGES": 2},
+]
+BP_VARIANTS = [{}, {"TSP_BP_NO_TMA": 1}, {"TSP_BP_ZPT": 1}, {"TSP_BP_ZPT": 4}, {"TSP_BP_ZPT": 8}, {"TSP_BP_ZPT": 16},
+               {"TSP_BP_ZPT": 32}]
+
+
+def _ids(v):
+    return "default" if not v else "-".join(f"{k[4:].lower()}{val}" for k, val in v.items())
+
+
+@pytest.mark.parametrize("variant", FP_VARIANTS, ids=_ids)
+@pytest.mark.parametrize("case", cases(), ids=lambda c: c[0])
+def test_fp_variant_matches_oracle(case, variant):
+    name, kind, vs, win, ds, vec = case
+    rng = np.random.default_rng(0)
+    x = rng.random(vs).astype(np.float32)
+    with env(**variant):
+        P, Q = make(kind, vs, win, ds, vec)
+        _, y = _run(P, 0, x, np.zeros(Q.proj_shape, np.float32))
+    ref = Q.fp(x.astype(np.float64))
+    assert rel_l2(y, ref) <= TOL, rel_l2(y, ref)
+
+
+@pytest.mark.parametrize("variant", BP_VARIANTS, ids=_ids)
+@pytest.mark.parametrize("case", cases(), ids=lambda c: c[0])
+def test_bp_variant_matches_oracle(case, variant):
+    name, kind, vs, win, ds, vec = case
+    rng = np.random.default_rng(0)
+    with env(**variant):
+        P, Q = make(kind, vs, win, ds, vec)
+        y = rng.random(Q.proj_shape).astype(np.float32)
+        x, _ = _run(P, 1, np.zeros(vs, np.float32), y)
+    ref = Q.bp(y.astype(np.float64))
+    assert rel_l2(x, ref) <= TOL, rel_l2(x, ref)
+
+
+def test_default_plan_uses_tma_kernels():
+    """The TMA-staged kernels are the ones that run for TMA-compatible shapes (no silent fallback)."""
+    name, kind, vs, win, ds, vec = cases()[0]
+    P, Q = make(kind, vs, win, ds, vec)
+    x = np.ones(vs, np.float32)
+    _, y = _run(P, 0, x, np.zeros(Q.proj_shape, np.float32))
+    assert P.info().fp_uses_tma == 1
+    _run(P, 1, x, y)
+    assert P.info().bp_uses_tma == 1
+    with env(TSP_FP_NO_TMA=1, TSP_BP_NO_TMA=1):
+        P2, _ = make(kind, vs, win, ds, vec)
+        _, y2 = _run(P2, 0, x, np.zeros(Q.proj_shape, np.float32))
+        assert P2.info().fp_uses_tma == 0
+        _run(P2, 1, x, y2)
+        assert P2.info().bp_uses_tma == 0
+
+
+def _cfg3_like(n, n_angles):
+    det = (n, 3 * n // 2)
+    vec = O.cone_vectors(np.linspace(0, 2 * np.pi, n_angles, endpoint=False), 2.8125 / det[1], 1.875 / det[0], 4.0, 2.0)
+    return O.CONE_VEC, (n, n, n), [(-.5, .5)] * 3, det, vec
+
+
+def test_variants_agree_at_256():
+    """cfg-3 geometry at 256^3 x 90 angles (too slow for the fp64 oracle in a unit test): TMA-staged and
+    plain-load kernels must agree to fp32 summation-order noise, in both directions."""
+    import torch
+    from tomosipo_b200 import _backend as B
+
+    kind, vs, win, ds, vec = _cfg3_like(256, 90)
+    torch.manual_seed(0)
+    x = torch.rand(vs, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    outs = []
+    for variant in ({}, {"TSP_FP_NO_TMA": 1, "TSP_BP_NO_TMA": 1}, {"TSP_FP_R": 4, "TSP_BP_ZPT": 16}):
+        with env(**variant):
+            P = B.Projector(kind, vs, win, ds, vec)
+            y = torch.empty(P.proj_shape, device="cuda")
+            xb = torch.empty(P.vol_shape, device="cuda")
+            P.project(B.FP, False, x.data_ptr(), y.data_ptr(), B.MEM_DEVICE, 0, s)
+            P.project(B.BP, False, xb.data_ptr(), y.data_ptr(), B.MEM_DEVICE, 0, s)
+            torch.cuda.synchronize()
+        outs.append((y.double(), xb.double()))
+    for y, xb in outs[1:]:
+        assert float((y - outs[0][0]).norm() / outs[0][0].norm()) <= 2e-6
+        assert float((xb - outs[0][1]).norm() / outs[0][1].norm()) <= 2e-6
+    # linearity at full kernel size: A(2x + x') == 2 A(x) + A(x')
+    with env():
+        P = B.Projector(kind, vs, win, ds, vec)
+        x2 = torch.rand(vs, device="cuda")
+        ya, yb, yc = (torch.empty(P.proj_shape, device="cuda") for _ in range(3))
+        xs = 2 * x + x2
+        for src, dst in ((x, ya), (x2, yb), (xs, yc)):
+            P.project(B.FP, False, src.data_ptr(), dst.data_ptr(), B.MEM_DEVICE, 0, s)
+        torch.cuda.synchronize()
+        lin = (2 * ya + yb).double()
+        assert float((yc.double() - lin).norm() / lin.norm()) <= 2e-6

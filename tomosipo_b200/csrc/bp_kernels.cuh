@@ -46,7 +46,17 @@ struct BPArgs {
     // register and re-adds it in front of every shared-memory tap (3 extra instructions per update).
     uint32_t magic_off;
     uint32_t magic_off_b;  // same for the alternative pitch
+    // fused SIRT update (tsp_sirt): when set, vol[i] -= epi_mul[i] * value instead of a plain store
+    const float *epi_mul;
 };
+
+// The one place a voxel value is written: SET, ADD, or the fused SIRT update.
+__device__ __forceinline__ void bp_store_one(const BPArgs &P, size_t idx, float v)
+{
+    float *dst = P.vol + idx;
+    if (P.epi_mul) *dst = *dst - __ldg(P.epi_mul + idx) * v;
+    else *dst = P.additive ? *dst + v : v;
+}
 
 // Per-(tile, angle) set-up result, tile-local: for a voxel at offset
 // (dx, dy, dz) from the tile centre,
@@ -306,9 +316,7 @@ __device__ __forceinline__ void bp_store(const BPArgs &P, int x, int y, int z0, 
     for (int i = 0; i < ZPT; ++i) {
         const int z = z0 + i;
         if (z < P.nz) {
-            float *dst = P.vol + ((size_t)z * P.ny + y) * P.nx + x;
-            const float v = acc[i] * P.out_scale;
-            *dst = P.additive ? *dst + v : v;
+            bp_store_one(P, ((size_t)z * P.ny + y) * P.nx + x, acc[i] * P.out_scale);
         }
     }
 }
@@ -575,8 +583,7 @@ __global__ void __launch_bounds__(256) bp_supersample_kernel(const BPArgs P)
                 }
     }
     acc *= P.out_scale / (float)(ss * ss * ss);
-    float *dst = P.vol + ((size_t)z * P.ny + y) * P.nx + x;
-    *dst = P.additive ? *dst + acc : acc;
+    bp_store_one(P, ((size_t)z * P.ny + y) * P.nx + x, acc);
 }
 
 }  // namespace tsp

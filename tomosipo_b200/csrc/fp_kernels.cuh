@@ -32,7 +32,18 @@ struct FPArgs {
     float sigma_m;        // voxel size along the march axis
     float rp2, rq2;       // (sigma_p / sigma_m)^2, (sigma_q / sigma_m)^2
     int offsets_fit_32bit;  // volume has < 2^31 elements: the interior loop may use 32-bit offsets
+    // fused SIRT residual (tsp_sirt): when set, the stored value is epi_mul[i] * (value - epi_sub[i])
+    const float *epi_sub;
+    const float *epi_mul;
 };
+
+// The one place a projection value is written: SET, ADD, or the fused SIRT residual.
+__device__ __forceinline__ void fp_store(const FPArgs &P, size_t idx, float val)
+{
+    if (P.epi_mul) val = __ldg(P.epi_mul + idx) * (val - __ldg(P.epi_sub + idx));
+    float *dst = P.proj + idx;
+    *dst = P.additive ? *dst + val : val;
+}
 
 __device__ __forceinline__ int warp_min_i(int v)
 {
@@ -197,10 +208,7 @@ __global__ void __launch_bounds__(FP_BU *FP_BV) fp_kernel(const FPArgs P)
         }
     }
     if (SUPERSAMPLE) sum /= (float)(ss * ss);
-    if (live) {
-        float *dst = P.proj + ((size_t)iv * P.n_angles + a) * P.det_u + iu;
-        *dst = P.additive ? *dst + sum : sum;
-    }
+    if (live) fp_store(P, ((size_t)iv * P.n_angles + a) * P.det_u + iu, sum);
 }
 
 // ---------------------------------------------------------------------------
@@ -348,8 +356,7 @@ __global__ void __launch_bounds__(FP_BU * FP_BV) fp_cols_kernel(const FPArgs P)
     for (int r = 0; r < R; ++r) {
         if (live_u && iv0 + r < P.det_v) {
             const float val = live[r] ? acc[r] * scale[r] : 0.0f;
-            float *dst = P.proj + ((size_t)(iv0 + r) * P.n_angles + a) * P.det_u + iu;
-            *dst = P.additive ? *dst + val : val;
+            fp_store(P, ((size_t)(iv0 + r) * P.n_angles + a) * P.det_u + iu, val);
         }
     }
 }

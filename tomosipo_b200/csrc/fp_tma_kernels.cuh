@@ -314,8 +314,7 @@ fp_tma_kernel(const FPTmaArgs A, const TensorMapBlob *__restrict__ tmap)
                 const float apr = ap[COLS ? 0 : r];
                 const float scale = P.sigma_m * sqrtf(1.0f + apr * apr * P.rp2 + aq[r] * aq[r] * P.rq2);
                 const float val = acc[r] * scale;
-                float *dst = P.proj + ((size_t)(iv0 + r) * P.n_angles + a) * P.det_u + iu;
-                *dst = P.additive ? *dst + val : val;
+                fp_store(P, ((size_t)(iv0 + r) * P.n_angles + a) * P.det_u + iu, val);
             }
         }
     }

@@ -218,6 +218,12 @@ static void plan_fp_tma_group(const tsp_projector *pr, FPGroup &grp)
         }
     }
     box_w = (box_w + 3) / 4 * 4;  // TMA boxes are whole 16-byte units
+    // test hook: an undersized box makes the kernel flag slices as unfit and sample them from
+    // global memory (the results must not change)
+    if (const char *e = getenv("TSP_FP_BOX_SHRINK")) {
+        box_w = std::max(8, box_w - 4 * atoi(e));
+        box_h = std::max(3, box_h - atoi(e));
+    }
     if (box_w < 8) box_w = 8;
     if (box_w > 256 || box_h > 256) return;                 // TMA box limit
     if ((size_t)box_w * box_h * 4 > 32 * 1024) return;      // keep >= 3 ring stages
@@ -435,7 +441,7 @@ static int launch_fp_tma_one(dim3 grid, size_t smem, cudaStream_t stream, const 
 }
 
 static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float *proj, int additive,
-                     cudaStream_t stream)
+                     cudaStream_t stream, const float *epi_sub = nullptr, const float *epi_mul = nullptr)
 {
     const tsp_geometry &g = pr->g;
     const int n[3] = {g.nx, g.ny, g.nz};
@@ -470,6 +476,7 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
         P.proj = proj;
         P.det_u = g.det_cols; P.det_v = g.det_rows; P.n_angles = g.n_angles;
         P.additive = additive;
+        P.epi_sub = epi_sub; P.epi_mul = epi_mul;
         P.det_ss = g.detector_supersampling;
         P.sigma_m = (float)pr->sigma[grp.march];
         const double rp = pr->sigma[grp.p_axis] / pr->sigma[grp.march];
@@ -495,9 +502,10 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
                 if (!bw[1] && (r == 24 || r == 28)) bw[1] = w;
             }
             if (getenv("TSP_FP_ONE_PITCH")) bw[0] = bw[1] = grp.box_w;
-            // a much wider box costs more L2 traffic than the conflicts it avoids
-            if (bw[0] > std::min(bw[1], grp.box_w) + 16) bw[0] = bw[1];
-            if (bw[1] > std::min(bw[0], grp.box_w) + 16) bw[1] = bw[0];
+            // (the wider box costs L2 -> shared traffic, which has headroom: 26 % of the crossbar peak
+            // at cfg 3, while the shared-memory pipe is the busiest unit of this kernel)
+            if (!bw[0]) bw[0] = bw[1] ? bw[1] : grp.box_w;
+            if (!bw[1]) bw[1] = bw[0];
             if (bw[0] > 256 || bw[1] > 256) bw[0] = bw[1] = grp.box_w;
             TensorMapBlob tmap[2];
             bool ok = true;
@@ -710,7 +718,7 @@ static int launch_bp_tma_variant(bool cone, int zpt, dim3 grid, cudaStream_t str
 }
 
 static int launch_bp(tsp_projector *pr, DeviceState *st, float *vol, const float *proj, int additive,
-                     cudaStream_t stream)
+                     cudaStream_t stream, const float *epi_mul = nullptr)
 {
     const tsp_geometry &g = pr->g;
     BPArgs P;
@@ -723,6 +731,7 @@ static int launch_bp(tsp_projector *pr, DeviceState *st, float *vol, const float
     P.vox_ss = g.voxel_supersampling;
     P.magic_off = 0;
     P.magic_off_b = 0;
+    P.epi_mul = epi_mul;
     const bool cone = g.kind == TSP_KIND_CONE_VEC;
     int used_tma = 0;
     if (g.voxel_supersampling > 1) {
@@ -830,19 +839,6 @@ extern "C" int tsp_project(tsp_projector *pr, int direction, int additive, void 
 }
 
 // ------------------------------------------------------------------- SIRT --
-__global__ void sirt_residual_kernel(float *__restrict__ y_tmp, const float *__restrict__ y,
-                                     const float *__restrict__ R, size_t n)
-{
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        y_tmp[i] = R[i] * (y_tmp[i] - y[i]);
-}
-__global__ void sirt_update_kernel(float *__restrict__ x, const float *__restrict__ x_tmp,
-                                   const float *__restrict__ C, size_t n)
-{
-    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
-        x[i] -= C[i] * x_tmp[i];
-}
-
 extern "C" int tsp_sirt(tsp_projector *pr, void *x, const void *y, const void *R, const void *C, void *y_tmp,
                         int iterations, int device, void *cuda_stream)
 {
@@ -859,19 +855,18 @@ extern "C" int tsp_sirt(tsp_projector *pr, void *x, const void *y, const void *R
     const tsp_geometry &g = pr->g;
     const size_t nvox = (size_t)g.nx * g.ny * g.nz;
     const size_t npix = (size_t)g.det_rows * g.n_angles * g.det_cols;
-    float *x_tmp = nullptr;
-    CUDA_TRY(cudaMallocAsync(&x_tmp, nvox * sizeof(float), stream));
+    // Each iteration is two launches of the projection kernels with fused epilogues:
+    //   FP stores   y_tmp = R * (A x - y)        (fp_store)
+    //   BP stores   x    -= C * (A^T y_tmp)      (bp_store_one)
+    // so the residual / update passes of the reference loop (README.md:162-163,
+    // notebooks/sirt_benchmark.py:130-136) cost no extra HBM traffic.
     int rc = TSP_OK;
     for (int it = 0; it < iterations && rc == TSP_OK; ++it) {
-        rc = launch_fp(pr, st, (const float *)x, (float *)y_tmp, 0, stream);
+        rc = launch_fp(pr, st, (const float *)x, (float *)y_tmp, 0, stream, (const float *)y, (const float *)R);
         if (rc) break;
-        sirt_residual_kernel<<<148 * 8, 256, 0, stream>>>((float *)y_tmp, (const float *)y, (const float *)R, npix);
-        rc = launch_bp(pr, st, x_tmp, (const float *)y_tmp, 0, stream);
-        if (rc) break;
-        sirt_update_kernel<<<148 * 8, 256, 0, stream>>>((float *)x, x_tmp, (const float *)C, nvox);
-        pr->launches += 2;
+        rc = launch_bp(pr, st, (float *)x, (const float *)y_tmp, 0, stream, (const float *)C);
     }
-    cudaFreeAsync(x_tmp, stream);
+    (void)nvox; (void)npix;
     if (rc == TSP_OK) CUDA_TRY(cudaGetLastError());
     return rc;
 }
