@@ -12,7 +12,11 @@ Contract: ``python bench.py --gpus N --steps K --warmup W`` prints ONE JSON line
              arrays (H2D + kernels + D2H inside the timed region).
 * roofline   for the dominant kernel: algorithmic bytes 4*(vol + proj) per
              launch over its measured duration, against the measured HBM peak;
-             `interp` adds the in-SM interpolation view (updates/clk/SM).
+             `traffic` = DRAM bytes per launch from the committed ncu capture
+             (profiles/r01_traffic.json); `interp` adds the in-SM interpolation
+             view (updates/clk/SM) that actually bounds these kernels.
+* sirt       SIRT iterations/s on the same problem (BASELINE.json metric, second
+             half): fused tsp_sirt at N = 1, sharded loop at N > 1.
 * cpu_baseline / --impl reference: the CPU restatement (oracle/, fp32,
              OpenMP, all host cores) on a bounded sample of the same workload.
              ASTRA -- the reference's engine -- has no CPU 3-D projector and is
@@ -43,6 +47,15 @@ def workload(n=512, n_angles=720):
     vg = ts.volume(shape=n, size=1)
     pg = ts.cone(angles=n_angles, shape=(n, 3 * n // 2), size=(1.875, 2.8125), src_orig_dist=4, src_det_dist=6).to_vec()
     return vg, pg
+
+
+def load_traffic():
+    """DRAM bytes per launch of the two hot kernels, from the committed `ncu --set full` capture."""
+    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return json.load(f)
+    return {}
 
 
 def load_peaks():
@@ -257,14 +270,53 @@ def run_ours(args):
     h2d = 4 * (nvox + npix) * world   # FP: volume in; BP: projections in
     d2h = 4 * (npix + nvox) * world   # FP: projections out; BP: volume out
 
+    # ---- SIRT iterations / s on the same problem (device-resident)
+    sirt_iters = max(2, min(args.steps, 5))
+    if world == 1:
+        from tomosipo_b200.algorithms import _weights
+
+        # weights R = 1/A(1), C = 1/A^T(1) are set-up (notebooks/sirt_benchmark.py:116-128); iterations are timed
+        R_, C_ = _weights(A, y, ts.epsilon)
+        xs = torch.zeros_like(xb); y_tmp = torch.empty_like(y)
+        strm = torch.cuda.current_stream().cuda_stream
+        P.sirt(xs.data_ptr(), y.data_ptr(), R_.data_ptr(), C_.data_ptr(), y_tmp.data_ptr(), 1, device=local, stream=strm)
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        P.sirt(xs.data_ptr(), y.data_ptr(), R_.data_ptr(), C_.data_ptr(), y_tmp.data_ptr(), sirt_iters, device=local,
+               stream=strm)
+        e1.record()
+        torch.cuda.synchronize()
+        sirt_ms = e0.elapsed_time(e1) / sirt_iters
+        del xs, y_tmp, R_, C_
+    else:
+        from tomosipo_b200.distributed import sirt as sirt_sharded
+
+        sirt_sharded(S, y, 1)
+        torch.cuda.synchronize()
+        dist.barrier()
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        sirt_sharded(S, y, sirt_iters)
+        e1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # includes the two set-up projections (R, C): count them as one extra iteration
+        sirt_ms = float(t.item()) / (sirt_iters + 1)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
     peaks, peak_kind = load_peaks()
+    traffic = load_traffic()
     b_alg = 4.0 * (nvox + npix)  # bytes per FP or per BP launch (SET mode), SURVEY.md 8d
-    dom = "bp_kernel" if bp_ms >= fp_ms else "fp_kernel"
+    info = P.info()
+    bp_name = "bp_tma_kernel" if info.bp_uses_tma else "bp_kernel"
+    fp_name = "fp_tma_kernel" if info.fp_uses_tma else "fp_cols_kernel"
+    dom = bp_name if bp_ms >= fp_ms else fp_name
     dom_ms = max(bp_ms, fp_ms)
     achieved = b_alg / (dom_ms * 1e-3) / 1e9
     sm_mhz = (clocks or {}).get("sm_mhz") or peaks.get("sm_max_mhz", 1965.0)
@@ -274,8 +326,10 @@ def run_ours(args):
         "fp_updates_per_clk_per_sm": upd / (fp_ms * 1e-3) / (sm_mhz * 1e6) / 148,
         "bp_updates_per_clk_per_sm": upd / (bp_ms * 1e-3) / (sm_mhz * 1e6) / 148,
         "ceiling_updates_per_clk_per_sm": 8.0,
-        "ceiling_note": "shared-memory gather: 32 words/clk/SM / 4 taps (SURVEY.md 8d planning figure)",
+        "ceiling_note": "shared-memory gather: 128 B/clk/SM / (4 taps x 4 B) (measured LDS crossbar rate, B300_MICROARCH.md)",
+        "fp_kernel": fp_name, "bp_kernel": bp_name,
     }
+    t_dom = traffic.get(dom) if world == 1 else None
     cpu_gups, cpu_dt, sample = cpu_sample()
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -287,11 +341,13 @@ def run_ours(args):
                    f"angle-sharded x{world}, z-slab volume: all_gather -> FP; BP -> NCCL reduce_scatter"},
         "fp_ms": fp_ms, "bp_ms": bp_ms,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_kind": peak_kind,
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": t_dom, "peak_kind": peak_kind,
                      "algorithmic_bytes_per_launch": b_alg, "interp": interp},
         "cpu_baseline": {"value": cpu_gups, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
+        "sirt": {"iters_per_s": 1e3 / sirt_ms, "ms_per_iter": sirt_ms, "iterations": sirt_iters,
+                 "path": "tsp_sirt (fused epilogues)" if world == 1 else "sharded loop (all_gather / reduce_scatter)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
