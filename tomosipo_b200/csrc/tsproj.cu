@@ -16,6 +16,7 @@
 #include "bp_kernels.cuh"
 #include "fp_kernels.cuh"
 #include "fp_tma_kernels.cuh"
+#include "thin_kernels.cuh"
 #include "tsp_internal.h"
 
 using namespace tsp;
@@ -441,19 +442,31 @@ static int launch_fp_tma_one(dim3 grid, size_t smem, cudaStream_t stream, const 
 }
 
 static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float *proj, int additive,
-                     cudaStream_t stream, const float *epi_sub = nullptr, const float *epi_mul = nullptr)
+                     cudaStream_t stream, const float *epi_sub = nullptr, const float *epi_mul = nullptr, int batch = 1)
 {
     const tsp_geometry &g = pr->g;
     const int n[3] = {g.nx, g.ny, g.nz};
     const size_t nvox = (size_t)g.nx * g.ny * g.nz;
+    const size_t npix = (size_t)g.det_rows * g.n_angles * g.det_cols;
+    // thin detectors (cfg 5 slabs): one launch per angle group covers the whole batch (thin_kernels.cuh)
+    const bool thin = g.det_rows <= THIN_MAX && g.detector_supersampling == 1 && !getenv("TSP_NO_THIN") &&
+                      (long long)batch * g.det_rows <= 65535;
+    if (!thin && batch > 1) {
+        for (int b = 0; b < batch; ++b)
+            if (int rc = launch_fp(pr, st, vol + b * nvox, proj + b * npix, additive, stream,
+                                   epi_sub ? epi_sub + b * npix : nullptr, epi_mul ? epi_mul + b * npix : nullptr, 1))
+                return rc;
+        return TSP_OK;
+    }
 
     bool need_t = false;
     for (const FPGroup &grp : pr->groups) need_t |= grp.transposed;
     float *vol_t = nullptr;
     const int ny_pad = (g.ny + 3) / 4 * 4;  // row pitch of the transposed copy: whole 16-byte units (TMA stride rule)
     if (need_t) {
-        CUDA_TRY(cudaMallocAsync(&vol_t, (size_t)g.nz * g.nx * ny_pad * sizeof(float), stream));
-        dim3 grid((g.nx + 31) / 32, (g.ny + 31) / 32, g.nz), block(32, 8);
+        CUDA_TRY(cudaMallocAsync(&vol_t, (size_t)batch * g.nz * g.nx * ny_pad * sizeof(float), stream));
+        if ((long long)g.nz * batch > 65535) return fail(TSP_ERR_INVALID, "nz * batch exceeds the transpose grid");
+        dim3 grid((g.nx + 31) / 32, (g.ny + 31) / 32, g.nz * batch), block(32, 8);  // batch items are contiguous planes
         transpose_xy_kernel<<<grid, block, 0, stream>>>(vol, vol_t, g.nx, g.ny, ny_pad);
         ++pr->launches;
     }
@@ -486,6 +499,18 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
         P.offsets_fit_32bit = (size_t)g.nz * g.nx * std::max(g.ny, ny_pad) < (1ull << 31) ? 1 : 0;
         const bool cone = g.kind == TSP_KIND_CONE_VEC;
         const bool ss = g.detector_supersampling > 1;
+        if (thin) {
+            P.det_ss = 1;
+            const int na = (int)grp.angles.size();
+            if ((na + THIN_FP_ANGLES - 1) / THIN_FP_ANGLES > 65535) return fail(TSP_ERR_INVALID, "too many angles for the thin FP grid");
+            dim3 tgrid((g.det_cols + 31) / 32, (na + THIN_FP_ANGLES - 1) / THIN_FP_ANGLES, batch * g.det_rows);
+            dim3 tblock(32, THIN_FP_ANGLES);
+            const size_t vstride = grp.transposed ? (size_t)g.nz * g.nx * ny_pad : nvox;
+            if (cone) fp_thin_kernel<true><<<tgrid, tblock, 0, stream>>>(P, na, vstride, npix);
+            else fp_thin_kernel<false><<<tgrid, tblock, 0, stream>>>(P, na, vstride, npix);
+            ++pr->launches;
+            continue;
+        }
         // ---- TMA-staged kernel (default): needs a 16-byte aligned base and row pitch
         if (!ss && grp.box_w > 0 && !getenv("TSP_FP_NO_TMA") && grp.pairs.size() / 2 <= 65535) {
             const int n_second = grp.transposed ? g.nx : g.ny;  // layout dims: (p, second, nz)
@@ -718,9 +743,20 @@ static int launch_bp_tma_variant(bool cone, int zpt, dim3 grid, cudaStream_t str
 }
 
 static int launch_bp(tsp_projector *pr, DeviceState *st, float *vol, const float *proj, int additive,
-                     cudaStream_t stream, const float *epi_mul = nullptr)
+                     cudaStream_t stream, const float *epi_mul = nullptr, int batch = 1)
 {
     const tsp_geometry &g = pr->g;
+    const size_t nvox_b = (size_t)g.nx * g.ny * g.nz;
+    const size_t npix_b = (size_t)g.det_rows * g.n_angles * g.det_cols;
+    // thin volumes (cfg 5 slabs): one launch covers the whole batch (thin_kernels.cuh)
+    const bool thin = g.nz <= THIN_MAX && g.voxel_supersampling == 1 && !getenv("TSP_NO_THIN") && batch <= 65535;
+    if (!thin && batch > 1) {
+        for (int b = 0; b < batch; ++b)
+            if (int rc = launch_bp(pr, st, vol + b * nvox_b, proj + b * npix_b, additive, stream,
+                                   epi_mul ? epi_mul + b * nvox_b : nullptr, 1))
+                return rc;
+        return TSP_OK;
+    }
     BPArgs P;
     P.proj = proj; P.vol = vol;
     P.nx = g.nx; P.ny = g.ny; P.nz = g.nz;
@@ -734,7 +770,13 @@ static int launch_bp(tsp_projector *pr, DeviceState *st, float *vol, const float
     P.epi_mul = epi_mul;
     const bool cone = g.kind == TSP_KIND_CONE_VEC;
     int used_tma = 0;
-    if (g.voxel_supersampling > 1) {
+    if (thin) {
+        const int gy = (g.ny + BP_TY - 1) / BP_TY;
+        if (gy > 65535) return fail(TSP_ERR_INVALID, "volume too large for the BP grid");
+        dim3 grid((g.nx + BP_TX - 1) / BP_TX, gy, batch), block(BP_TX, BP_TY);
+        if (cone) bp_thin_kernel<true><<<grid, block, 0, stream>>>(P, nvox_b, npix_b);
+        else bp_thin_kernel<false><<<grid, block, 0, stream>>>(P, nvox_b, npix_b);
+    } else if (g.voxel_supersampling > 1) {
         if (g.nz > 65535) return fail(TSP_ERR_INVALID, "voxel supersampling supports nz <= 65535");
         dim3 grid((g.nx + 31) / 32, (g.ny + 7) / 8, g.nz), block(32, 8);
         if (cone) bp_supersample_kernel<true><<<grid, block, 0, stream>>>(P);
@@ -820,10 +862,8 @@ extern "C" int tsp_project(tsp_projector *pr, int direction, int additive, void 
             CUDA_TRY(cudaMemcpyAsync(dproj, proj, npix * batch * sizeof(float), cudaMemcpyHostToDevice, stream));
     }
     int rc = TSP_OK;
-    for (int b = 0; b < batch && rc == TSP_OK; ++b) {
-        if (direction == TSP_FP) rc = launch_fp(pr, st, dvol + b * nvox, dproj + b * npix, additive, stream);
-        else rc = launch_bp(pr, st, dvol + b * nvox, dproj + b * npix, additive, stream);
-    }
+    if (direction == TSP_FP) rc = launch_fp(pr, st, dvol, dproj, additive, stream, nullptr, nullptr, batch);
+    else rc = launch_bp(pr, st, dvol, dproj, additive, stream, nullptr, batch);
     if (memory_kind == TSP_MEM_HOST) {
         if (rc == TSP_OK) {
             if (direction == TSP_FP)
