@@ -252,6 +252,32 @@ __device__ __forceinline__ void bp_tile_loop_zinv(uint32_t sbase, float nu, floa
     const uint32_t cbase = sbase + magic_off + 4u * __float_as_uint(ru);
     float fv = nv * r;
     const float dv = sv * r;
+    if (ZPT % 2 == 0) {
+        // Two voxels of the run per step with Blackwell's packed fp32x2 arithmetic (FFMA2 / FADD2:
+        // two independent fp32 operations per issue slot - the kernel is issue-bound): 10.5
+        // instead of 16 instructions per update.  Every pair (.x, .y) = (voxel i, voxel i + 1).
+        const float2 M2 = make_float2(BP_MAGIC, BP_MAGIC), NEG1 = make_float2(-1.0f, -1.0f);
+        const float2 wu2 = make_float2(wu, wu), w22 = make_float2(w2, w2), step2 = make_float2(2.0f * dv, 2.0f * dv);
+        float2 fv2 = make_float2(fv, fv + dv);
+#pragma unroll
+        for (int i = 0; i < ZPT; i += 2) {
+            const float2 rv2 = __fadd2_rd(fv2, M2);                       // round-down add == floor
+            const float2 wv2 = __fadd2_rn(fv2, __ffma2_rn(rv2, NEG1, M2));  // fv - (rv - M)
+            const uint32_t a0 = __float_as_uint(rv2.x) * (uint32_t)(4 * PITCH) + cbase;
+            const uint32_t a1 = __float_as_uint(rv2.y) * (uint32_t)(4 * PITCH) + cbase;
+            const float2 p00 = make_float2(lds_f32<0>(a0), lds_f32<0>(a1));
+            const float2 p10 = make_float2(lds_f32<4>(a0), lds_f32<4>(a1));
+            const float2 p01 = make_float2(lds_f32<4 * PITCH>(a0), lds_f32<4 * PITCH>(a1));
+            const float2 p11 = make_float2(lds_f32<4 * PITCH + 4>(a0), lds_f32<4 * PITCH + 4>(a1));
+            const float2 lo = __ffma2_rn(wu2, __ffma2_rn(p00, NEG1, p10), p00);
+            const float2 hi = __ffma2_rn(wu2, __ffma2_rn(p01, NEG1, p11), p01);
+            const float2 val = __ffma2_rn(wv2, __ffma2_rn(lo, NEG1, hi), lo);
+            const float2 a2 = __ffma2_rn(w22, val, make_float2(acc[i], acc[i + 1]));
+            acc[i] = a2.x; acc[i + 1] = a2.y;
+            fv2 = __fadd2_rn(fv2, step2);
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < ZPT; ++i) {
         const float rv = __fadd_rd(fv, BP_MAGIC);

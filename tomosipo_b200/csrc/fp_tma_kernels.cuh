@@ -106,9 +106,11 @@ __device__ __forceinline__ void fpt_slice_box(const FPRay (&c)[8], float t, floa
 // uniform register, so the second tap row is addressed as [a0 + UR]).
 template <bool COLS, int V, int R>
 __device__ __forceinline__ void fpt_consume(const FPTmaArgs &A, int kA, int kD, float t0, uint32_t ctrl, uint32_t full,
-                                            uint32_t empty, int lane, const float *ap, const float *cp,
-                                            const float (&aq)[R], const float (&cq)[R], float (&acc)[R])
+                                            uint32_t empty, int lane, const float2 *ap2, const float2 *cp2,
+                                            const float2 (&aq2)[R / 2], const float2 (&cq2)[R / 2], float2 (&acc2)[R / 2])
 {
+    // rows are kept as packed pairs (.x, .y) = (row 2h, row 2h + 1); with COLS, ap2[0].x / cp2[0].x hold
+    // the column's shared p line
     const FPArgs &P = A.a;
     const float MAGIC = 12582912.0f;
     const uint32_t bw4 = (uint32_t)A.box_w[V] * 4u;
@@ -120,37 +122,51 @@ __device__ __forceinline__ void fpt_consume(const FPTmaArgs &A, int kA, int kD, 
         uint32_t sb, fit;
         asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(sb), "=r"(fit) : "r"(ctrl + 8u * s) : "memory");
         if (fit) {
-            float wp = 0.0f;
-            uint32_t offp = 0u;
+            // Two detector rows per step with Blackwell's packed fp32x2 arithmetic (FFMA2 / FADD2: two
+            // independent fp32 operations per issue slot - the kernel is issue-bound): 10.5 instead
+            // of 16 instructions per sample.  Every pair (.x, .y) = (row r, row r + 1).
+            const float2 M2 = make_float2(MAGIC, MAGIC), NEG1 = make_float2(-1.0f, -1.0f), t2 = make_float2(t, t);
+            float2 wp2 = make_float2(0.0f, 0.0f);
+            uint32_t offp0 = 0u, offp1 = 0u;
             if (COLS) {
-                const float fp = fmaf(ap[0], t, cp[0]);
+                const float fp = fmaf(ap2[0].x, t, cp2[0].x);
                 const float rp = __fadd_rd(fp, MAGIC);
-                wp = fp - (rp - MAGIC);
-                offp = __float_as_uint(rp) * 4u + sb;
+                const float wp = fp - (rp - MAGIC);
+                wp2 = make_float2(wp, wp);
+                offp0 = offp1 = __float_as_uint(rp) * 4u + sb;
             }
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
+            for (int h = 0; h < R / 2; ++h) {
                 if (!COLS) {
-                    const float fp = fmaf(ap[COLS ? 0 : r], t, cp[COLS ? 0 : r]);
-                    const float rp = __fadd_rd(fp, MAGIC);
-                    wp = fp - (rp - MAGIC);
-                    offp = __float_as_uint(rp) * 4u + sb;
+                    const float2 fp2 = __ffma2_rn(ap2[COLS ? 0 : h], t2, cp2[COLS ? 0 : h]);
+                    const float2 rp2 = __fadd2_rd(fp2, M2);
+                    wp2 = __fadd2_rn(fp2, __ffma2_rn(rp2, NEG1, M2));
+                    offp0 = __float_as_uint(rp2.x) * 4u + sb;
+                    offp1 = __float_as_uint(rp2.y) * 4u + sb;
                 }
-                const float fq = fmaf(aq[r], t, cq[r]);
-                const float rq = __fadd_rd(fq, MAGIC);
-                const float wq = fq - (rq - MAGIC);
-                const uint32_t a0 = __float_as_uint(rq) * bw4 + offp;
-                const uint32_t a1 = a0 + bw4;
-                const float v00 = fpt_lds<0>(a0), v10 = fpt_lds<4>(a0);
-                const float v01 = fpt_lds<0>(a1), v11 = fpt_lds<4>(a1);
-                const float lo = fmaf(wp, v10 - v00, v00);
-                const float hi = fmaf(wp, v11 - v01, v01);
-                acc[r] += fmaf(wq, hi - lo, lo);
+                const float2 fq2 = __ffma2_rn(aq2[h], t2, cq2[h]);
+                const float2 rq2 = __fadd2_rd(fq2, M2);                          // round-down add == floor
+                const float2 wq2 = __fadd2_rn(fq2, __ffma2_rn(rq2, NEG1, M2));  // fq - (rq - M)
+                const uint32_t a0 = __float_as_uint(rq2.x) * bw4 + offp0;
+                const uint32_t b0 = __float_as_uint(rq2.y) * bw4 + offp1;
+                const uint32_t a1 = a0 + bw4, b1 = b0 + bw4;
+                const float2 v00 = make_float2(fpt_lds<0>(a0), fpt_lds<0>(b0));
+                const float2 v10 = make_float2(fpt_lds<4>(a0), fpt_lds<4>(b0));
+                const float2 v01 = make_float2(fpt_lds<0>(a1), fpt_lds<0>(b1));
+                const float2 v11 = make_float2(fpt_lds<4>(a1), fpt_lds<4>(b1));
+                const float2 lo = __ffma2_rn(wp2, __ffma2_rn(v00, NEG1, v10), v00);
+                const float2 hi = __ffma2_rn(wp2, __ffma2_rn(v01, NEG1, v11), v01);
+                const float2 val = __ffma2_rn(wq2, __ffma2_rn(lo, NEG1, hi), lo);
+                acc2[h] = __fadd2_rn(acc2[h], val);
             }
         } else {
 #pragma unroll
-            for (int r = 0; r < R; ++r)
-                careful_range(P, ap[COLS ? 0 : r], aq[r], cp[COLS ? 0 : r], cq[r], t0, k, k + 1, acc[r]);
+            for (int h = 0; h < R / 2; ++h) {
+                careful_range(P, COLS ? ap2[0].x : ap2[COLS ? 0 : h].x, aq2[h].x, COLS ? cp2[0].x : cp2[COLS ? 0 : h].x,
+                              cq2[h].x, t0, k, k + 1, acc2[h].x);
+                careful_range(P, COLS ? ap2[0].x : ap2[COLS ? 0 : h].y, aq2[h].y, COLS ? cp2[0].x : cp2[COLS ? 0 : h].y,
+                              cq2[h].y, t0, k, k + 1, acc2[h].y);
+            }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + 8u * s);
@@ -293,27 +309,32 @@ fp_tma_kernel(const FPTmaArgs A, const TensorMapBlob *__restrict__ tmap)
     // out-of-detector lanes / rows shadow the tile's last pixel: their taps stay inside the staged box
     const double cu = (double)min(iu, u1) + 0.5;
 
-    float ap[COLS ? 1 : R], cp[COLS ? 1 : R], aq[R], cq[R], acc[R];
+    float2 ap2[COLS ? 1 : R / 2], cp2[COLS ? 1 : R / 2], aq2[R / 2], cq2[R / 2], acc2[R / 2];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const double cv = (double)min(iv0 + r, v1) + 0.5;
-        const FPRay ray = fpt_ray<CONE>(g, cu, cv, P.n_p, P.n_q);
-        if (!COLS || r == 0) { ap[COLS ? 0 : r] = ray.ap; cp[COLS ? 0 : r] = ray.cp; }
-        aq[r] = ray.aq; cq[r] = ray.cq;
-        acc[r] = 0.0f;
+    for (int h = 0; h < R / 2; ++h) {
+        const FPRay r0 = fpt_ray<CONE>(g, cu, (double)min(iv0 + 2 * h, v1) + 0.5, P.n_p, P.n_q);
+        const FPRay r1 = fpt_ray<CONE>(g, cu, (double)min(iv0 + 2 * h + 1, v1) + 0.5, P.n_p, P.n_q);
+        if (!COLS || h == 0) {
+            ap2[COLS ? 0 : h] = make_float2(r0.ap, r1.ap);
+            cp2[COLS ? 0 : h] = make_float2(r0.cp, r1.cp);
+        }
+        aq2[h] = make_float2(r0.aq, r1.aq);
+        cq2[h] = make_float2(r0.cq, r1.cq);
+        acc2[h] = make_float2(0.0f, 0.0f);
     }
     __syncthreads();
     const int kA = hull[0], kD = hull[1], variant = hull[2];
-    if (variant) fpt_consume<COLS, 1, R>(A, kA, kD, t0, ctrl, full, empty, lane, ap, cp, aq, cq, acc);
-    else fpt_consume<COLS, 0, R>(A, kA, kD, t0, ctrl, full, empty, lane, ap, cp, aq, cq, acc);
+    if (variant) fpt_consume<COLS, 1, R>(A, kA, kD, t0, ctrl, full, empty, lane, ap2, cp2, aq2, cq2, acc2);
+    else fpt_consume<COLS, 0, R>(A, kA, kD, t0, ctrl, full, empty, lane, ap2, cp2, aq2, cq2, acc2);
 
     if (slot_live && iu < P.det_u) {
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             if (iv0 + r < P.det_v) {
-                const float apr = ap[COLS ? 0 : r];
-                const float scale = P.sigma_m * sqrtf(1.0f + apr * apr * P.rp2 + aq[r] * aq[r] * P.rq2);
-                const float val = acc[r] * scale;
+                const float apr = COLS ? ap2[0].x : ((r & 1) ? ap2[COLS ? 0 : r / 2].y : ap2[COLS ? 0 : r / 2].x);
+                const float aqr = (r & 1) ? aq2[r / 2].y : aq2[r / 2].x;
+                const float scale = P.sigma_m * sqrtf(1.0f + apr * apr * P.rp2 + aqr * aqr * P.rq2);
+                const float val = ((r & 1) ? acc2[r / 2].y : acc2[r / 2].x) * scale;
                 fp_store(P, ((size_t)(iv0 + r) * P.n_angles + a) * P.det_u + iu, val);
             }
         }
