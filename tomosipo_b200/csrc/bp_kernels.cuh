@@ -46,6 +46,7 @@ struct BPArgs {
     // register and re-adds it in front of every shared-memory tap (3 extra instructions per update).
     uint32_t magic_off;
     uint32_t magic_off_b;  // same for the alternative pitch
+    int no_rows3;          // tuning aid (TSP_BP_NO_ROWS3): disable the 3-row z-invariant loop
     // fused SIRT update (tsp_sirt): when set, vol[i] -= epi_mul[i] * value instead of a plain store
     const float *epi_mul;
 };
@@ -95,7 +96,7 @@ __device__ __forceinline__ float bp_sample_global(const float *__restrict__ proj
 // box; shuffles reduce the bounding box; lane 0 writes the local map.
 __device__ __forceinline__ void bp_setup(const BPArgs &P, const BPAngle *__restrict__ ang, int corner,
                                          double xc, double yc, double zc, double hx, double hy,
-                                         double hz, int max_rows, int max_cols, int alt_cols, int u_align, BPLocal *out)
+                                         double hz, int max_rows, int max_cols, int alt_cols, int u_align, bool allow_rows3, BPLocal *out)
 {
     const double den_c = ang->dn[0] * xc + ang->dn[1] * yc + ang->dn[2] * zc + ang->dn[3];
     const double nu_c = ang->nu[0] * xc + ang->nu[1] * yc + ang->nu[2] * zc + ang->nu[3];
@@ -178,6 +179,14 @@ __device__ __forceinline__ void bp_setup(const BPArgs &P, const BPAngle *__restr
     // detectors whose rows are parallel to the z axis (all circular geometries).
     const double au2 = ang->nu[2] - off_u * ang->dn[2];
     L.z_invariant = ((fabs(au2) + 64.0 * fabs(ang->dn[2])) * (2.0 * hz + 1.0) < 1e-7 * fabs(den_c)) ? 1 : 0;
+    if (L.z_invariant && mode != BP_GLOBAL && mode != BP_SKIP && allow_rows3) {
+        // row step per voxel, dv = av2 / den, largest where |den| is smallest on the tile; the 3-row
+        // loop also reads row j+2 of the last voxel pair: one spare row must fit the staged box
+        const double av2 = ang->nv[2] - off_v * ang->dn[2];
+        const double dvmax = fabs(av2) / fmin(fabs(dmin), fabs(dmax));
+        const bool positive = (av2 >= 0.0) == (den_c > 0.0);
+        if (positive && dvmax <= 0.9999 && wv + 1 <= max_rows) L.z_invariant = 2;
+    }
     L.pad = 0;
     *out = L;
 }
@@ -293,6 +302,50 @@ __device__ __forceinline__ void bp_tile_loop_zinv(uint32_t sbase, float nu, floa
     }
 }
 
+// z-invariant angles whose row coordinate advances by 0 <= dv <= 1 per voxel (the detector
+// pixel is at least as tall as a projected voxel - every configuration of BASELINE.json):
+// voxel i + 1 samples row pair (j, j+1) or (j+1, j+2) of voxel i's row j, so a pair of voxels
+// needs 3 rows x 2 columns = 6 shared-memory taps instead of 8.  The kernel is bound by the
+// shared-memory pipe after the packed-arithmetic rewrite; this trades two taps for one select.
+template <bool CONE, int ZPT, int PITCH>
+__device__ __forceinline__ void bp_tile_loop_zinv3(uint32_t sbase, float nu, float nv, float dn, float sv,
+                                                   float wpar, uint32_t magic_off, float (&acc)[ZPT])
+{
+    static_assert(ZPT % 2 == 0, "pairs of voxels");
+    float r = 1.0f, w2 = wpar;
+    if (CONE) { r = rcp_approx(dn); w2 = r * r; }
+    const float fu = nu * r;
+    const float ru = __fadd_rd(fu, BP_MAGIC);
+    const float wu = fu - (ru - BP_MAGIC);
+    const uint32_t cbase = sbase + magic_off + 4u * __float_as_uint(ru);
+    const float fv = nv * r;
+    const float dv = sv * r;
+    const float2 M2 = make_float2(BP_MAGIC, BP_MAGIC), NEG1 = make_float2(-1.0f, -1.0f);
+    const float2 wu2 = make_float2(wu, wu), w22 = make_float2(w2, w2), step2 = make_float2(2.0f * dv, 2.0f * dv);
+    float2 fv2 = make_float2(fv, fv + dv);
+#pragma unroll
+    for (int i = 0; i < ZPT; i += 2) {
+        const float2 rv2 = __fadd2_rd(fv2, M2);
+        const float2 wv2 = __fadd2_rn(fv2, __ffma2_rn(rv2, NEG1, M2));
+        const uint32_t a = __float_as_uint(rv2.x) * (uint32_t)(4 * PITCH) + cbase;
+        const bool next_row = __float_as_uint(rv2.y) != __float_as_uint(rv2.x);
+        // rows j, j+1 (packed) and j+2 (scalar), two columns each
+        const float2 p0 = make_float2(lds_f32<0>(a), lds_f32<4 * PITCH>(a));
+        const float2 p1 = make_float2(lds_f32<4>(a), lds_f32<4 * PITCH + 4>(a));
+        const float q0 = lds_f32<8 * PITCH>(a), q1 = lds_f32<8 * PITCH + 4>(a);
+        const float2 h01 = __ffma2_rn(wu2, __ffma2_rn(p0, NEG1, p1), p0);   // (h(j), h(j+1))
+        const float h2 = fmaf(wu, q1 - q0, q0);                             // h(j+2)
+        const float2 h12 = make_float2(h01.y, h2);
+        const float2 d = __ffma2_rn(h01, NEG1, h12);                        // (h1 - h0, h2 - h1)
+        float2 val = __ffma2_rn(wv2, d, h01);                               // (voxel i, voxel i+1 if it moved on a row)
+        const float same = fmaf(wv2.y, d.x, h01.x);                         // voxel i+1 if it stayed on row j
+        val.y = next_row ? val.y : same;
+        const float2 a2 = __ffma2_rn(w22, val, make_float2(acc[i], acc[i + 1]));
+        acc[i] = a2.x; acc[i + 1] = a2.y;
+        fv2 = __fadd2_rn(fv2, step2);
+    }
+}
+
 // One angle's contribution to a thread's z run.  `L` lives in shared memory;
 // `sbase` is the shared byte address of the staged footprint (row pitch PITCH).
 template <bool CONE, int ZPT, int PITCH, int PITCH_B>
@@ -308,10 +361,12 @@ __device__ __forceinline__ void bp_accumulate_angle(const BPArgs &P, const BPLoc
     const float su = L.au[2], sv = L.av[2], sd = L.ad[2];
     const float wpar = L.weight;
     if (mode == BP_SMEM) {
-        if (L.z_invariant) bp_tile_loop_zinv<CONE, ZPT, PITCH>(sbase, nu, nv, dn, sv, wpar, P.magic_off, acc);
+        if (ZPT % 2 == 0 && L.z_invariant == 2) bp_tile_loop_zinv3<CONE, (ZPT % 2 == 0 ? ZPT : 2), PITCH>(sbase, nu, nv, dn, sv, wpar, P.magic_off, reinterpret_cast<float (&)[(ZPT % 2 == 0 ? ZPT : 2)]>(acc));
+        else if (L.z_invariant) bp_tile_loop_zinv<CONE, ZPT, PITCH>(sbase, nu, nv, dn, sv, wpar, P.magic_off, acc);
         else bp_tile_loop<CONE, false, ZPT, PITCH>(sbase, nu, nv, dn, su, sv, sd, 0.0f, 0.0f, wpar, P.magic_off, acc);
     } else if (PITCH_B != PITCH && mode == BP_SMEM_B) {
-        if (L.z_invariant) bp_tile_loop_zinv<CONE, ZPT, PITCH_B>(sbase, nu, nv, dn, sv, wpar, P.magic_off_b, acc);
+        if (ZPT % 2 == 0 && L.z_invariant == 2) bp_tile_loop_zinv3<CONE, (ZPT % 2 == 0 ? ZPT : 2), PITCH_B>(sbase, nu, nv, dn, sv, wpar, P.magic_off_b, reinterpret_cast<float (&)[(ZPT % 2 == 0 ? ZPT : 2)]>(acc));
+        else if (L.z_invariant) bp_tile_loop_zinv<CONE, ZPT, PITCH_B>(sbase, nu, nv, dn, sv, wpar, P.magic_off_b, acc);
         else bp_tile_loop<CONE, false, ZPT, PITCH_B>(sbase, nu, nv, dn, su, sv, sd, 0.0f, 0.0f, wpar, P.magic_off_b, acc);
     } else if (mode == BP_SMEM_CLAMP) {
         bp_tile_loop<CONE, true, ZPT, PITCH>(sbase, nu, nv, dn, su, sv, sd, (float)L.wu - 1.5f, (float)L.wv - 1.5f,
@@ -383,7 +438,7 @@ __global__ void __launch_bounds__(BP_THREADS) bp_kernel(const BPArgs P)
             const int j = tid >> 3;
             // clamp so that all 8 lanes of a group take part in the shuffles
             const int a = a0 + min(j, na - 1);
-            bp_setup(P, P.angles + a, tid & 7, xc, yc, zc, hx, hy, hz, BP_WV, BP_WU, 0, 1, &loc[j]);
+            bp_setup(P, P.angles + a, tid & 7, xc, yc, zc, hx, hy, hz, BP_WV, BP_WU, 0, 1, false, &loc[j]);
         }
         __syncthreads();
         // stage footprints: warps over rows, lanes over columns
@@ -528,7 +583,7 @@ bp_tma_kernel(const BPArgs P, const TensorMapBlob *__restrict__ tmap)  // tmap[0
         for (int a0 = 0; a0 < P.n_angles; a0 += 4) {
             const int a = min(a0 + group, P.n_angles - 1);
             BPLocal L;
-            bp_setup(P, P.angles + a, corner, xc, yc, zc, hx, hy, hz, WV, BP_TMA_PITCH, BP_TMA_PITCH_B, 4, &L);  // valid in corner-0 lanes
+            bp_setup(P, P.angles + a, corner, xc, yc, zc, hx, hy, hz, WV, BP_TMA_PITCH, BP_TMA_PITCH_B, 4, !P.no_rows3, &L);  // valid in corner-0 lanes
             for (int g = 0; g < 4 && a0 + g < P.n_angles; ++g) {
                 const int angle = a0 + g;
                 mbar_wait(empty + 8u * s, parity);

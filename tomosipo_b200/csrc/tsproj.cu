@@ -767,6 +767,7 @@ static int launch_bp(tsp_projector *pr, DeviceState *st, float *vol, const float
     P.vox_ss = g.voxel_supersampling;
     P.magic_off = 0;
     P.magic_off_b = 0;
+    P.no_rows3 = getenv("TSP_BP_NO_ROWS3") ? 1 : 0;
     P.epi_mul = epi_mul;
     const bool cone = g.kind == TSP_KIND_CONE_VEC;
     int used_tma = 0;
