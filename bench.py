@@ -75,8 +75,9 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.index = index
-        self.samples = []
+        self.samples = []   # (arrival time, csv line)
         self.proc = None
+        self.window = None  # (t0, t1) of the timed region; samples before it were taken under warm-up load
 
     def start(self):
         try:
@@ -90,7 +91,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append(line.strip())
+            self.samples.append((time.time(), line.strip()))
 
     def stop(self):
         if not self.proc:
@@ -102,7 +103,12 @@ class ClockSampler:
             self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        lines = [s for t, s in self.samples if self.window and self.window[0] <= t <= self.window[1] + 0.15]
+        scope = "timed region"
+        if len(lines) < 2:  # region shorter than the sampling period: use every sample taken under load (warm-up + timed)
+            lines = [s for t, s in self.samples]
+            scope = "warm-up + timed region"
+        for s in lines:
             f = [x.strip() for x in s.split(",")]
             if len(f) < 7:
                 continue
@@ -114,7 +120,13 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "scope": scope, "reasons": sorted(reasons)}
+
+
+def omp_threads():
+    """Threads the OpenMP oracle actually uses (torchrun exports OMP_NUM_THREADS=1 to its children)."""
+    v = os.environ.get("OMP_NUM_THREADS")
+    return int(v) if v and v.isdigit() else (os.cpu_count() or 1)
 
 
 def cpu_sample(n=192, n_angles=96, repeats=1):
@@ -142,7 +154,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    cores = os.cpu_count() or 1
+    # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1); set before the OpenMP runtime starts
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
+    cores = omp_threads()
     for _ in range(args.warmup):
         cpu_sample(96, 48)
     vals, ms = [], []
@@ -203,6 +217,9 @@ def run_ours(args):
     def bp():
         S.T(y, out=xb)
 
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
     for _ in range(max(args.warmup, 3)):
         fp()
         bp()
@@ -210,13 +227,11 @@ def run_ours(args):
 
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     launches0 = P.info().kernel_launches
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     t_begin = torch.cuda.Event(enable_timing=True); t_end = torch.cuda.Event(enable_timing=True)
+    wall0 = time.time()
     t_begin.record()
     for i in range(args.steps):
         ev[i][0].record()
@@ -226,6 +241,7 @@ def run_ours(args):
         ev[i][2].record()
     t_end.record()
     torch.cuda.synchronize()
+    sampler.window = (wall0, time.time())
     if world > 1:
         dist.barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -330,7 +346,10 @@ def run_ours(args):
         "fp_kernel": fp_name, "bp_kernel": bp_name,
     }
     t_dom = traffic.get(dom) if world == 1 else None
-    cpu_gups, cpu_dt, sample = cpu_sample()
+    cpu_base = None
+    if world == 1:  # rank 0 at N = 1 only
+        cpu_gups, cpu_dt, sample = cpu_sample()
+        cpu_base = {"value": cpu_gups, "unit": UNIT, "cores": omp_threads(), "kind": "port", "sample": sample}
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -343,7 +362,7 @@ def run_ours(args):
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": t_dom, "peak_kind": peak_kind,
                      "algorithmic_bytes_per_launch": b_alg, "interp": interp},
-        "cpu_baseline": {"value": cpu_gups, "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "cpu_baseline": cpu_base,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "steps": e2e_steps},
         "sirt": {"iters_per_s": 1e3 / sirt_ms, "ms_per_iter": sirt_ms, "iterations": sirt_iters,
