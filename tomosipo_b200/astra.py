@@ -184,8 +184,24 @@ def backward(*data, voxel_supersampling=1, detector_supersampling=1, projector=N
 
 
 def fdk(vol_data, proj_data, *, voxel_supersampling=1, detector_supersampling=1):
-    """FDK reconstruction (``tomosipo/astra.py:374-406``): not on the projection hot path.
+    """FDK reconstruction of ``proj_data`` into ``vol_data`` (``tomosipo/astra.py:374-406``).
 
-    Listed as a "next" row in SURVEY.md 8f (ramp filter + FDK-weighted BP); not built yet.
+    The reference calls ``astra.experimental.accumulate_FDK``; here: cosine weighting and ramp
+    filter on the GPU (:func:`tomosipo_b200.algorithms.fdk`), then the library's backprojector.
+    The result overwrites the volume dataset's array.
     """
-    raise NotImplementedError("ts.astra.fdk is outside the projection hot path and is not implemented yet.")
+    import numpy as np
+
+    from .algorithms import fdk as _fdk
+
+    op = ts.operator(vol_data.geometry, proj_data.geometry, voxel_supersampling=voxel_supersampling,
+                     detector_supersampling=detector_supersampling)
+    rec = _fdk(op, proj_data.data)
+    dst = vol_data.data
+    if isinstance(dst, np.ndarray):
+        dst[...] = rec if isinstance(rec, np.ndarray) else rec.cpu().numpy()
+    else:
+        import torch
+
+        dst.copy_(torch.as_tensor(rec).to(dst.device))
+    return vol_data
