@@ -103,6 +103,7 @@ typedef struct tsp_projector_info {
     int32_t bp_uses_tma;                      /* last BP used TMA-staged footprints */
     int32_t fp_uses_transpose;                /* last FP built an (x<->y) transposed volume */
     int32_t fp_uses_tma;                      /* last FP used the TMA-staged kernel for >= 1 angle group */
+    int32_t host_pipelined;                   /* last TSP_MEM_HOST call ran the chunked copy/compute pipeline */
 } tsp_projector_info;
 int tsp_projector_get_info(const tsp_projector *projector, tsp_projector_info *info);
 

@@ -54,6 +54,7 @@ class tsp_projector_info(ctypes.Structure):
         ("bp_uses_tma", ctypes.c_int32),
         ("fp_uses_transpose", ctypes.c_int32),
         ("fp_uses_tma", ctypes.c_int32),
+        ("host_pipelined", ctypes.c_int32),
     ]
 
 

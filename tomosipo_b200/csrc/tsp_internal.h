@@ -62,6 +62,8 @@ struct DeviceState {
     std::vector<size_t> pair_offset;  // in pairs
     BPAngle *bp_angles = nullptr;  // [n_angles]
     std::vector<size_t> list_offset;
+    // host-array pipeline (tsp_project with TSP_MEM_HOST): copy-in / copy-out streams
+    cudaStream_t s_in = nullptr, s_out = nullptr;
 };
 
 }  // namespace tsp
@@ -80,4 +82,14 @@ struct tsp_projector {
     int bp_uses_tma = 0;
     int fp_uses_transpose = 0;
     int fp_uses_tma = 0;
+    // Host-array pipeline: the problem cut into sub-problems (BP: z-slabs of the volume with the
+    // detector rows their cone shadow covers; FP: detector row blocks), each with its own
+    // sub-projector, so that H2D / D2H of one chunk overlaps the kernels of another.
+    struct HostChunk {
+        tsp_projector *sub = nullptr;
+        int z0 = 0, z1 = 0, v0 = 0, v1 = 0;
+    };
+    std::vector<HostChunk> host_bp, host_fp;
+    bool host_planned = false;
+    int host_pipelined = 0;  // last host-array call ran the chunked pipeline
 };

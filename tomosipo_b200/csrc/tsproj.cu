@@ -253,7 +253,16 @@ static int validate(const tsp_geometry *g)
     return TSP_OK;
 }
 
+static int create_projector_internal(const tsp_geometry *geometry, const int *axes_override, tsp_projector **out);
+
 extern "C" int tsp_projector_create(const tsp_geometry *geometry, tsp_projector **out)
+{
+    return create_projector_internal(geometry, nullptr, out);
+}
+
+// axes_override: per-angle FP marching axes to use instead of picking them from the central ray
+// (sub-projectors of the host pipeline must march like their parent, whose central ray differs)
+static int create_projector_internal(const tsp_geometry *geometry, const int *axes_override, tsp_projector **out)
 {
     if (!out) return fail(TSP_ERR_INVALID, "out is NULL");
     *out = nullptr;
@@ -277,7 +286,7 @@ extern "C" int tsp_projector_create(const tsp_geometry *geometry, tsp_projector 
         NormAngle na;
         normalise_angle(pr, a, na);
         build_bp_angle(g, na, pr->bp_angles[a]);
-        const int m = pick_marching_axis(g.kind, na);
+        const int m = axes_override ? axes_override[a] : pick_marching_axis(g.kind, na);
         pr->march_axis[a] = m;
         // The in-slice axis the warp's lanes (det_u) run along must be the
         // contiguous one: x in the native (z,y,x) layout, y in the (z,x,y) copy.
@@ -323,6 +332,8 @@ static void free_device_state(tsp_projector *pr)
         cudaFree(kv.second.fp_pairs);
         cudaFree(kv.second.bp_angles);
         cudaFree(kv.second.tmap_ring);
+        if (kv.second.s_in) cudaStreamDestroy(kv.second.s_in);
+        if (kv.second.s_out) cudaStreamDestroy(kv.second.s_out);
     }
     cudaSetDevice(cur);
     pr->dev.clear();
@@ -331,6 +342,10 @@ static void free_device_state(tsp_projector *pr)
 extern "C" void tsp_projector_destroy(tsp_projector *pr)
 {
     if (!pr) return;
+    for (auto &c : pr->host_bp) tsp_projector_destroy(c.sub);
+    for (auto &c : pr->host_fp) tsp_projector_destroy(c.sub);
+    pr->host_bp.clear();
+    pr->host_fp.clear();
     if (!pr->dev.empty()) free_device_state(pr);
     delete pr;
 }
@@ -350,6 +365,7 @@ extern "C" int tsp_projector_get_info(const tsp_projector *pr, tsp_projector_inf
     info->bp_uses_tma = pr->bp_uses_tma;
     info->fp_uses_transpose = pr->fp_uses_transpose;
     info->fp_uses_tma = pr->fp_uses_tma;
+    info->host_pipelined = pr->host_pipelined;
     return TSP_OK;
 }
 
@@ -829,6 +845,187 @@ struct DeviceGuard {
     }
 };
 
+
+// ------------------------------------------------- host-array pipeline ----
+// What ASTRA's CompositeGeometryManager does for host arrays (reference doc/topics/operator.rst:226-261;
+// SURVEY.md 8f rank 4): cut the job into sub-problems so that transfers overlap the kernels.
+//   BP: z-slabs of the volume; slab k needs only the detector rows its cone shadow covers, which are
+//       contiguous in the (v, angle, u) layout -> H2D rows(k) | BP_k | D2H slab(k) run as a 3-stage pipeline;
+//   FP: the volume is uploaded once, then detector row blocks -> FP_j | D2H rows(j).
+// Every sub-problem is an ordinary projector on a sub-geometry (same vectors, shifted detector centre,
+// cropped volume window) that marches along its parent's axes, so the results are those of the
+// single-shot path up to fp32 summation order.
+static tsp_projector *make_sub_projector(const tsp_projector *pr, int z0, int z1, int v0, int v1)
+{
+    tsp_geometry g = pr->g;
+    std::vector<double> vec = pr->vectors;
+    const double sz = pr->sigma[2];
+    g.nz = z1 - z0;
+    g.win_min[2] = pr->g.win_min[2] + z0 * sz;
+    g.win_max[2] = pr->g.win_min[2] + z1 * sz;
+    g.det_rows = v1 - v0;
+    const double shift = 0.5 * (v0 + v1) - 0.5 * pr->g.det_rows;  // new detector centre, in rows from the old one
+    for (int a = 0; a < g.n_angles; ++a)
+        for (int i = 0; i < 3; ++i) vec[12 * (size_t)a + 3 + i] += shift * vec[12 * (size_t)a + 9 + i];
+    g.vectors = vec.data();
+    tsp_projector *sub = nullptr;
+    if (create_projector_internal(&g, pr->march_axis.data(), &sub) != TSP_OK) return nullptr;
+    return sub;
+}
+
+// detector rows [v0, v1) that voxels of the slab z0 <= z < z1 can touch (bilinear taps included)
+static void slab_row_range(const tsp_projector *pr, int z0, int z1, int &v0, int &v1)
+{
+    const tsp_geometry &g = pr->g;
+    double lo = 1e300, hi = -1e300;
+    bool all = false;
+    for (int a = 0; a < g.n_angles && !all; ++a) {
+        const BPAngle &m = pr->bp_angles[a];
+        int sign = 0;
+        for (int c = 0; c < 8; ++c) {
+            const double x = (c & 1) ? 0.5 * g.nx : -0.5 * g.nx, y = (c & 2) ? 0.5 * g.ny : -0.5 * g.ny;
+            const double z = ((c & 4) ? z1 : z0) - 0.5 * g.nz;
+            const double den = m.dn[0] * x + m.dn[1] * y + m.dn[2] * z + m.dn[3];
+            const int sg = den > 0 ? 1 : -1;
+            if (den == 0.0 || (sign && sg != sign)) { all = true; break; }
+            sign = sg;
+            const double v = (m.nv[0] * x + m.nv[1] * y + m.nv[2] * z + m.nv[3]) / den;
+            if (!std::isfinite(v)) { all = true; break; }
+            lo = std::min(lo, v); hi = std::max(hi, v);
+        }
+    }
+    if (all) { v0 = 0; v1 = g.det_rows; return; }
+    v0 = (int)std::max(0.0, std::floor(lo) - 2.0);
+    v1 = (int)std::min((double)g.det_rows, std::ceil(hi) + 2.0);
+    if (v1 <= v0) { v0 = std::min(std::max(v0, 0), g.det_rows - 1); v1 = v0 + 1; }  // shadow off the detector
+}
+
+static int chunk_size(int n)
+{
+    int c = (n + 7) / 8;
+    c = (c + 31) / 32 * 32;
+    return std::max(32, c);
+}
+
+static bool plan_host_pipeline(tsp_projector *pr)
+{
+    std::lock_guard<std::mutex> lock(pr->mu);
+    if (pr->host_planned) return !pr->host_bp.empty();
+    pr->host_planned = true;
+    const tsp_geometry &g = pr->g;
+    if (g.nz < 64 || g.det_rows < 64) return false;
+    const int cz = chunk_size(g.nz), cv = chunk_size(g.det_rows);
+    std::vector<tsp_projector::HostChunk> bp, fp;
+    bool ok = true;
+    for (int z0 = 0; z0 < g.nz && ok; z0 += cz) {
+        tsp_projector::HostChunk c;
+        c.z0 = z0; c.z1 = std::min(g.nz, z0 + cz);
+        slab_row_range(pr, c.z0, c.z1, c.v0, c.v1);
+        c.sub = make_sub_projector(pr, c.z0, c.z1, c.v0, c.v1);
+        ok = c.sub != nullptr;
+        bp.push_back(c);
+    }
+    for (int v0 = 0; v0 < g.det_rows && ok; v0 += cv) {
+        tsp_projector::HostChunk c;
+        c.z0 = 0; c.z1 = g.nz; c.v0 = v0; c.v1 = std::min(g.det_rows, v0 + cv);
+        c.sub = make_sub_projector(pr, 0, g.nz, c.v0, c.v1);
+        ok = c.sub != nullptr;
+        fp.push_back(c);
+    }
+    if (!ok) {
+        for (auto &c : bp) tsp_projector_destroy(c.sub);
+        for (auto &c : fp) tsp_projector_destroy(c.sub);
+        return false;
+    }
+    pr->host_bp = std::move(bp);
+    pr->host_fp = std::move(fp);
+    return true;
+}
+
+// One FP (SET) or BP (SET) between host arrays, chunked and pipelined over three streams.
+static int project_host_pipelined(tsp_projector *pr, DeviceState *st, int device, int direction, float *vol, float *proj,
+                                  cudaStream_t stream)
+{
+    const tsp_geometry &g = pr->g;
+    const size_t nvox = (size_t)g.nx * g.ny * g.nz, npix = (size_t)g.det_rows * g.n_angles * g.det_cols;
+    const size_t row = (size_t)g.n_angles * g.det_cols, slice = (size_t)g.nx * g.ny;
+    if (!st->s_in) CUDA_TRY(cudaStreamCreateWithFlags(&st->s_in, cudaStreamNonBlocking));
+    if (!st->s_out) CUDA_TRY(cudaStreamCreateWithFlags(&st->s_out, cudaStreamNonBlocking));
+    float *dvol = nullptr, *dproj = nullptr;
+    CUDA_TRY(cudaMallocAsync(&dvol, nvox * sizeof(float), stream));
+    CUDA_TRY(cudaMallocAsync(&dproj, npix * sizeof(float), stream));
+    const std::vector<tsp_projector::HostChunk> &chunks = direction == TSP_FP ? pr->host_fp : pr->host_bp;
+    std::vector<cudaEvent_t> ev_in(chunks.size()), ev_done(chunks.size());
+    cudaEvent_t ev_start;
+    CUDA_TRY(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
+    for (size_t k = 0; k < chunks.size(); ++k) {
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaEventRecord(ev_start, stream));  // buffers allocated, earlier work on `stream` ordered before us
+    CUDA_TRY(cudaStreamWaitEvent(st->s_in, ev_start, 0));
+    CUDA_TRY(cudaStreamWaitEvent(st->s_out, ev_start, 0));
+    int rc = TSP_OK;
+    if (direction == TSP_FP) {
+        CUDA_TRY(cudaMemcpyAsync(dvol, vol, nvox * sizeof(float), cudaMemcpyHostToDevice, stream));
+        for (size_t k = 0; k < chunks.size() && rc == TSP_OK; ++k) {
+            const auto &c = chunks[k];
+            DeviceState *sst = nullptr;
+            if ((rc = get_device_state(c.sub, device, &sst))) break;
+            const int64_t l0 = c.sub->launches;
+            rc = launch_fp(c.sub, sst, dvol, dproj + (size_t)c.v0 * row, 0, stream);
+            pr->launches += c.sub->launches - l0;
+            pr->fp_uses_tma = c.sub->fp_uses_tma; pr->fp_uses_transpose = c.sub->fp_uses_transpose;
+            if (rc) break;
+            CUDA_TRY(cudaEventRecord(ev_done[k], stream));
+            CUDA_TRY(cudaStreamWaitEvent(st->s_out, ev_done[k], 0));
+            CUDA_TRY(cudaMemcpyAsync(proj + (size_t)c.v0 * row, dproj + (size_t)c.v0 * row,
+                                     (size_t)(c.v1 - c.v0) * row * sizeof(float), cudaMemcpyDeviceToHost, st->s_out));
+        }
+    } else {
+        std::vector<char> uploaded(g.det_rows, 0);
+        for (size_t k = 0; k < chunks.size() && rc == TSP_OK; ++k) {
+            const auto &c = chunks[k];
+            // upload the rows of this chunk that no earlier chunk brought in (maximal runs)
+            for (int v = c.v0; v < c.v1;) {
+                if (uploaded[v]) { ++v; continue; }
+                int e = v;
+                while (e < c.v1 && !uploaded[e]) uploaded[e++] = 1;
+                CUDA_TRY(cudaMemcpyAsync(dproj + (size_t)v * row, proj + (size_t)v * row, (size_t)(e - v) * row * sizeof(float),
+                                         cudaMemcpyHostToDevice, st->s_in));
+                v = e;
+            }
+            CUDA_TRY(cudaEventRecord(ev_in[k], st->s_in));
+            CUDA_TRY(cudaStreamWaitEvent(stream, ev_in[k], 0));
+            DeviceState *sst = nullptr;
+            if ((rc = get_device_state(c.sub, device, &sst))) break;
+            const int64_t l0 = c.sub->launches;
+            rc = launch_bp(c.sub, sst, dvol + (size_t)c.z0 * slice, dproj + (size_t)c.v0 * row, 0, stream);
+            pr->launches += c.sub->launches - l0;
+            pr->bp_uses_tma = c.sub->bp_uses_tma;
+            if (rc) break;
+            CUDA_TRY(cudaEventRecord(ev_done[k], stream));
+            CUDA_TRY(cudaStreamWaitEvent(st->s_out, ev_done[k], 0));
+            CUDA_TRY(cudaMemcpyAsync(vol + (size_t)c.z0 * slice, dvol + (size_t)c.z0 * slice,
+                                     (size_t)(c.z1 - c.z0) * slice * sizeof(float), cudaMemcpyDeviceToHost, st->s_out));
+        }
+    }
+    // the user's stream completes after the copy-out stream; then everything is released
+    cudaEvent_t ev_out;
+    CUDA_TRY(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventRecord(ev_out, st->s_out));
+    CUDA_TRY(cudaStreamWaitEvent(stream, ev_out, 0));
+    cudaFreeAsync(dvol, stream);
+    cudaFreeAsync(dproj, stream);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    cudaStreamSynchronize(st->s_in);
+    for (size_t k = 0; k < chunks.size(); ++k) { cudaEventDestroy(ev_in[k]); cudaEventDestroy(ev_done[k]); }
+    cudaEventDestroy(ev_start);
+    cudaEventDestroy(ev_out);
+    if (rc == TSP_OK && e != cudaSuccess) return fail(TSP_ERR_CUDA, "host pipeline failed: %s", cudaGetErrorString(e));
+    return rc;
+}
+
 extern "C" int tsp_project(tsp_projector *pr, int direction, int additive, void *vol, void *proj, int batch,
                            int memory_kind, int device, void *cuda_stream)
 {
@@ -853,6 +1050,14 @@ extern "C" int tsp_project(tsp_projector *pr, int direction, int additive, void 
     const size_t npix = (size_t)g.det_rows * g.n_angles * g.det_cols;
 
     float *dvol = (float *)vol, *dproj = (float *)proj;
+    pr->host_pipelined = 0;
+    size_t pipeline_min = 64u << 20;  // smaller jobs: one upload, one launch, one download
+    if (const char *e = getenv("TSP_HOST_PIPELINE_MIN_MB")) pipeline_min = (size_t)atoll(e) << 20;
+    if (memory_kind == TSP_MEM_HOST && batch == 1 && !additive && (nvox + npix) * sizeof(float) >= pipeline_min &&
+        !getenv("TSP_HOST_NO_PIPELINE") && plan_host_pipeline(pr)) {
+        pr->host_pipelined = 1;
+        return project_host_pipelined(pr, st, device, direction, (float *)vol, (float *)proj, stream);
+    }
     if (memory_kind == TSP_MEM_HOST) {
         CUDA_TRY(cudaMallocAsync(&dvol, nvox * batch * sizeof(float), stream));
         CUDA_TRY(cudaMallocAsync(&dproj, npix * batch * sizeof(float), stream));
