@@ -851,7 +851,8 @@ struct DeviceGuard {
 // SURVEY.md 8f rank 4): cut the job into sub-problems so that transfers overlap the kernels.
 //   BP: z-slabs of the volume; slab k needs only the detector rows its cone shadow covers, which are
 //       contiguous in the (v, angle, u) layout -> H2D rows(k) | BP_k | D2H slab(k) run as a 3-stage pipeline;
-//   FP: the volume is uploaded once, then detector row blocks -> FP_j | D2H rows(j).
+//   FP: detector row blocks; block j needs only the slices its rays can reach (contiguous in z)
+//       -> H2D slices(j) | FP_j | D2H rows(j).
 // Every sub-problem is an ordinary projector on a sub-geometry (same vectors, shifted detector centre,
 // cropped volume window) that marches along its parent's axes, so the results are those of the
 // single-shot path up to fp32 summation order.
@@ -900,9 +901,80 @@ static void slab_row_range(const tsp_projector *pr, int z0, int z1, int &v0, int
     if (v1 <= v0) { v0 = std::min(std::max(v0, 0), g.det_rows - 1); v1 = v0 + 1; }  // shadow off the detector
 }
 
+
+// 2-D distance from point q to segment [a, b]
+static double dist_point_segment(const double q[2], const double a[2], const double b[2])
+{
+    const double ab[2] = {b[0] - a[0], b[1] - a[1]}, aq[2] = {q[0] - a[0], q[1] - a[1]};
+    const double l2 = ab[0] * ab[0] + ab[1] * ab[1];
+    double t = l2 > 0 ? (aq[0] * ab[0] + aq[1] * ab[1]) / l2 : 0.0;
+    t = std::min(1.0, std::max(0.0, t));
+    const double dx = aq[0] - t * ab[0], dy = aq[1] - t * ab[1];
+    return std::sqrt(dx * dx + dy * dy);
+}
+
+// volume slices [z0, z1) that rays of the detector rows v0 <= v < v1 can touch: a guaranteed bound
+// from the steepest / shallowest ray elevation of the block and the horizontal reach of the volume
+static void block_z_range(const tsp_projector *pr, int v0, int v1, int &z0, int &z1)
+{
+    const tsp_geometry &g = pr->g;
+    const double rxy = 0.5 * std::sqrt((double)g.nx * g.nx + (double)g.ny * g.ny) + 1.0;
+    double lo = 1e300, hi = -1e300;
+    bool all = false;
+    for (int a = 0; a < g.n_angles && !all; ++a) {
+        NormAngle n;
+        normalise_angle(pr, a, n);
+        double pix[4][3];
+        for (int c = 0; c < 4; ++c) {
+            const double cu = ((c & 1) ? g.det_cols : 0) - 0.5 * g.det_cols, cv = ((c & 2) ? v1 : v0) - 0.5 * g.det_rows;
+            for (int i = 0; i < 3; ++i) pix[c][i] = n.dc[i] + cu * n.u[i] + cv * n.v[i];
+        }
+        if (g.kind == TSP_KIND_CONE_VEC) {
+            const double *s = n.p;
+            double dzmin = 1e300, dzmax = -1e300, hmax = 0.0;
+            for (int c = 0; c < 4; ++c) {
+                dzmin = std::min(dzmin, pix[c][2] - s[2]); dzmax = std::max(dzmax, pix[c][2] - s[2]);
+                hmax = std::max(hmax, std::hypot(pix[c][0] - s[0], pix[c][1] - s[1]));
+            }
+            // min horizontal distance from the source to the block's parallelogram (corner order 0,1,3,2)
+            const int ord[4] = {0, 1, 3, 2};
+            double hmin = 1e300;
+            bool inside = true;
+            double sgn = 0.0;
+            for (int e = 0; e < 4; ++e) {
+                const double *p0 = pix[ord[e]], *p1 = pix[ord[(e + 1) & 3]];
+                hmin = std::min(hmin, dist_point_segment(s, p0, p1));
+                const double cr = (p1[0] - p0[0]) * (s[1] - p0[1]) - (p1[1] - p0[1]) * (s[0] - p0[0]);
+                if (cr != 0.0) { if (sgn == 0.0) sgn = cr; else if ((cr > 0) != (sgn > 0)) inside = false; }
+            }
+            const double ds = std::hypot(s[0], s[1]);
+            if (inside || hmin < 1e-9 * (hmax + 1.0)) { all = true; break; }
+            const double dnear = std::max(0.0, ds - rxy), dfar = ds + rxy;
+            const double slo = std::min(dzmin / hmin, dzmin / hmax), shi = std::max(dzmax / hmin, dzmax / hmax);
+            const double cand[4] = {slo * dnear, slo * dfar, shi * dnear, shi * dfar};
+            for (double c : cand) { lo = std::min(lo, s[2] + c); hi = std::max(hi, s[2] + c); }
+        } else {
+            const double *r = n.p;
+            const double h = std::hypot(r[0], r[1]);
+            if (h < 1e-9 * std::fabs(r[2])) { all = true; break; }
+            for (int c = 0; c < 4; ++c) {
+                const double reach = (std::hypot(pix[c][0], pix[c][1]) + rxy) / h * std::fabs(r[2]);
+                lo = std::min(lo, pix[c][2] - reach); hi = std::max(hi, pix[c][2] + reach);
+            }
+        }
+        if (!std::isfinite(lo) || !std::isfinite(hi)) all = true;
+    }
+    if (all) { z0 = 0; z1 = g.nz; return; }
+    z0 = (int)std::max(0.0, std::floor(lo + 0.5 * g.nz) - 2.0);
+    z1 = (int)std::min((double)g.nz, std::ceil(hi + 0.5 * g.nz) + 2.0);
+    if (z1 <= z0) { z0 = std::min(std::max(z0, 0), g.nz - 1); z1 = z0 + 1; }  // block sees nothing of the volume
+}
+
 static int chunk_size(int n)
 {
-    int c = (n + 7) / 8;
+    int k = 8;  // chunks per job; TSP_HOST_CHUNKS overrides (tuning aid)
+    if (const char *e = getenv("TSP_HOST_CHUNKS")) k = std::max(1, atoi(e));
+    int c = (n + k - 1) / k;
     c = (c + 31) / 32 * 32;
     return std::max(32, c);
 }
@@ -927,8 +999,9 @@ static bool plan_host_pipeline(tsp_projector *pr)
     }
     for (int v0 = 0; v0 < g.det_rows && ok; v0 += cv) {
         tsp_projector::HostChunk c;
-        c.z0 = 0; c.z1 = g.nz; c.v0 = v0; c.v1 = std::min(g.det_rows, v0 + cv);
-        c.sub = make_sub_projector(pr, 0, g.nz, c.v0, c.v1);
+        c.v0 = v0; c.v1 = std::min(g.det_rows, v0 + cv);
+        block_z_range(pr, c.v0, c.v1, c.z0, c.z1);
+        c.sub = make_sub_projector(pr, c.z0, c.z1, c.v0, c.v1);
         ok = c.sub != nullptr;
         fp.push_back(c);
     }
@@ -936,6 +1009,10 @@ static bool plan_host_pipeline(tsp_projector *pr)
         for (auto &c : bp) tsp_projector_destroy(c.sub);
         for (auto &c : fp) tsp_projector_destroy(c.sub);
         return false;
+    }
+    if (getenv("TSP_DEBUG")) {
+        for (auto &c : bp) fprintf(stderr, "[tsp] host BP chunk: z [%d, %d) <- rows [%d, %d)\n", c.z0, c.z1, c.v0, c.v1);
+        for (auto &c : fp) fprintf(stderr, "[tsp] host FP chunk: rows [%d, %d) <- z [%d, %d)\n", c.v0, c.v1, c.z0, c.z1);
     }
     pr->host_bp = std::move(bp);
     pr->host_fp = std::move(fp);
@@ -967,13 +1044,24 @@ static int project_host_pipelined(tsp_projector *pr, DeviceState *st, int device
     CUDA_TRY(cudaStreamWaitEvent(st->s_out, ev_start, 0));
     int rc = TSP_OK;
     if (direction == TSP_FP) {
-        CUDA_TRY(cudaMemcpyAsync(dvol, vol, nvox * sizeof(float), cudaMemcpyHostToDevice, stream));
+        std::vector<char> uploaded(g.nz, 0);
         for (size_t k = 0; k < chunks.size() && rc == TSP_OK; ++k) {
             const auto &c = chunks[k];
+            // upload the slices of this block's z range that no earlier block brought in (maximal runs)
+            for (int z = c.z0; z < c.z1;) {
+                if (uploaded[z]) { ++z; continue; }
+                int e = z;
+                while (e < c.z1 && !uploaded[e]) uploaded[e++] = 1;
+                CUDA_TRY(cudaMemcpyAsync(dvol + (size_t)z * slice, vol + (size_t)z * slice, (size_t)(e - z) * slice * sizeof(float),
+                                         cudaMemcpyHostToDevice, st->s_in));
+                z = e;
+            }
+            CUDA_TRY(cudaEventRecord(ev_in[k], st->s_in));
+            CUDA_TRY(cudaStreamWaitEvent(stream, ev_in[k], 0));
             DeviceState *sst = nullptr;
             if ((rc = get_device_state(c.sub, device, &sst))) break;
             const int64_t l0 = c.sub->launches;
-            rc = launch_fp(c.sub, sst, dvol, dproj + (size_t)c.v0 * row, 0, stream);
+            rc = launch_fp(c.sub, sst, dvol + (size_t)c.z0 * slice, dproj + (size_t)c.v0 * row, 0, stream);
             pr->launches += c.sub->launches - l0;
             pr->fp_uses_tma = c.sub->fp_uses_tma; pr->fp_uses_transpose = c.sub->fp_uses_transpose;
             if (rc) break;
