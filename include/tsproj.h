@@ -126,6 +126,20 @@ const char *tsp_last_error(void);
 int tsp_sirt(tsp_projector *projector, void *x, const void *y, const void *R, const void *C,
              void *y_tmp, int iterations, int device, void *cuda_stream);
 
+/*
+ * One half of that iteration on device-resident data, for callers that own the
+ * loop (the z-slab / angle-block sharded SIRT of tomosipo_b200/distributed.py,
+ * where a collective sits between the two halves):
+ *   TSP_FP:  proj = mul * (A vol - sub)   sub, mul: [det_rows][n_angles][det_cols]
+ *            (the `y_tmp = A(x); y_tmp -= y; y_tmp *= R` lines of
+ *            notebooks/sirt_benchmark.py:131-133 formed in the projector's store)
+ *   TSP_BP:  vol -= mul * (A^T proj)      mul: [nz][ny][nx]; sub must be NULL
+ *            (`x_tmp = A.T(y_tmp); x_tmp *= C; x -= x_tmp`, :134-136)
+ * Asynchronous on the stream.
+ */
+int tsp_project_fused(tsp_projector *projector, int direction, void *vol, void *proj, const void *sub,
+                      const void *mul, int device, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -75,8 +75,15 @@ def _worker(rank, world, port, tmpdir):
         torch.testing.assert_close(slab[: S.z_hi - S.z_lo], full_bp[S.z_lo:S.z_hi], rtol=1e-4, atol=1e-5)
         assert float(slab[S.z_hi - S.z_lo:].abs().sum()) == 0.0            # padding stays empty
         torch.testing.assert_close(S.gather_volume(slab), full_bp, rtol=1e-4, atol=1e-5)
+        # the slab-pipelined exchange (default for world > 1) against one reduce_scatter per call
+        S1 = ShardedOperator(vg, pg, make_local=OracleOperator, pipeline=False)
+        assert S.pipeline and not S1.pipeline
+        assert [(j, a, b) for j, a, b, _ in S.slab_operators()] == [(0, 0, 5), (1, 5, 9)]
+        torch.testing.assert_close(S1.T(w[:, lo:hi, :].contiguous()), slab, rtol=1e-5, atol=1e-6)
+        rec1 = S1.gather_volume(sirt(S1, y_full[:, lo:hi, :].contiguous(), 4))
         # SIRT: sharded == single-process
         rec = S.gather_volume(sirt(S, y_full[:, lo:hi, :].contiguous(), 4))
+        torch.testing.assert_close(rec, rec1, rtol=1e-4, atol=1e-5)
         torch.save(rec, os.path.join(tmpdir, f"rec{rank}.pt"))
         with pytest.raises(ValueError):
             S(torch.zeros(3, 3, 3))

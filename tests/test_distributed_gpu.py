@@ -32,7 +32,20 @@ def _worker(rank, world, port, tmpdir):
         assert torch.equal(y_blk, y_full[:, S.angle_lo:S.angle_hi, :])      # FP per angle is independent: bit-exact
         slab = S.T(w[:, S.angle_lo:S.angle_hi, :].contiguous())
         torch.testing.assert_close(S.gather_volume(slab), bp_full, rtol=1e-5, atol=1e-6)   # sum order differs
+        # slab-pipelined exchange (default) against one reduce_scatter per call
+        S1 = ShardedOperator(vg, pg, pipeline=False)
+        assert S.pipeline and not S1.pipeline
+        slab1 = S1.T(w[:, S.angle_lo:S.angle_hi, :].contiguous())
+        torch.testing.assert_close(slab1, slab, rtol=1e-5, atol=1e-6)
+        rec1 = S1.gather_volume(sirt(S1, y_full[:, S.angle_lo:S.angle_hi, :].contiguous(), 5))
         rec = S.gather_volume(sirt(S, y_full[:, S.angle_lo:S.angle_hi, :].contiguous(), 5))
+        assert float(torch.linalg.vector_norm(rec - rec1) / torch.linalg.vector_norm(rec1)) < 1e-5
+        # fused residual == explicit three passes
+        xf = x.contiguous()
+        yb = y_full[:, S.angle_lo:S.angle_hi, :].contiguous()
+        Rw = torch.rand(S.proj_shape, device="cuda", generator=g)
+        r_fused = S.residual(xf, yb, Rw, torch.empty_like(yb))
+        torch.testing.assert_close(r_fused, Rw * (S.local(xf) - yb), rtol=1e-5, atol=1e-6)
         if rank == 0:
             torch.save(rec.cpu(), os.path.join(tmpdir, "rec.pt"))
             # single-GPU SIRT with the same loop

@@ -183,6 +183,35 @@ def test_fused_sirt_matches_explicit_loop_and_oracle():
     assert isinstance(x_np, np.ndarray) and rel_l2(x_np, xq) <= 1e-4
 
 
+def test_project_fused_halves_match_explicit_passes():
+    """tsp_project_fused: FP store forms mul * (A x - sub), BP store forms x -= mul * A^T y
+    (the two halves of tsp_sirt, used by the sharded SIRT)."""
+    import torch
+    import tomosipo_b200 as ts
+    from tomosipo_b200 import _backend as B
+
+    vg = ts.volume(shape=(40, 36, 44), size=(1.0, 0.9, 1.1))
+    pg = ts.cone(angles=19, shape=(40, 60), size=(2.0, 3.0), src_orig_dist=4, src_det_dist=7)
+    A = ts.operator(vg, pg)
+    P = A.astra_projector
+    g = torch.Generator(device="cuda").manual_seed(1)
+    x = torch.rand(A.domain_shape, device="cuda", generator=g)
+    y = torch.rand(A.range_shape, device="cuda", generator=g)
+    R = torch.rand(A.range_shape, device="cuda", generator=g)
+    C = torch.rand(A.domain_shape, device="cuda", generator=g)
+    s = torch.cuda.current_stream().cuda_stream
+    r = torch.empty_like(y)
+    P.project_fused(B.FP, x.data_ptr(), r.data_ptr(), y.data_ptr(), R.data_ptr(), device=0, stream=s)
+    torch.testing.assert_close(r, R * (A(x) - y), rtol=1e-5, atol=1e-6)
+    x2 = x.clone()
+    P.project_fused(B.BP, x2.data_ptr(), r.data_ptr(), None, C.data_ptr(), device=0, stream=s)
+    torch.testing.assert_close(x2, x - C * A.T(r), rtol=1e-5, atol=1e-5)
+    with pytest.raises(ValueError):
+        P.project_fused(B.FP, x.data_ptr(), r.data_ptr(), None, R.data_ptr(), device=0, stream=s)
+    with pytest.raises(ValueError):
+        P.project_fused(B.BP, x.data_ptr(), r.data_ptr(), y.data_ptr(), C.data_ptr(), device=0, stream=s)
+
+
 @pytest.mark.parametrize("kindname", ["par_slab", "cone_thin"])
 def test_thin_batched_matches_oracle_per_item(kindname):
     """cfg-5 shapes: a batch of thin volumes in ONE C-ABI call (tsp_project(batch=B), thin_kernels.cuh)

@@ -70,6 +70,7 @@ EXPORTED_SYMBOLS = (
     "tsp_version",
     "tsp_last_error",
     "tsp_sirt",
+    "tsp_project_fused",
 )
 
 
@@ -119,6 +120,8 @@ def lib():
         L.tsp_last_error.restype = ctypes.c_char_p
         L.tsp_sirt.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.c_int, vp]
         L.tsp_sirt.restype = ctypes.c_int
+        L.tsp_project_fused.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, vp]
+        L.tsp_project_fused.restype = ctypes.c_int
         _lib = L
         return _lib
 
@@ -192,6 +195,12 @@ class Projector:
         vp = ctypes.c_void_p
         _check(lib().tsp_sirt(self._handle, vp(x_ptr), vp(y_ptr), vp(r_ptr), vp(c_ptr), vp(ytmp_ptr),
                               int(iterations), int(device), vp(stream)))
+
+    def project_fused(self, direction, vol_ptr, proj_ptr, sub_ptr, mul_ptr, device=0, stream=0):
+        """``proj = mul * (A vol - sub)`` (FP) or ``vol -= mul * A^T proj`` (BP, ``sub_ptr`` = None) on device pointers."""
+        vp = ctypes.c_void_p
+        _check(lib().tsp_project_fused(self._handle, int(direction), vp(vol_ptr), vp(proj_ptr), vp(sub_ptr), vp(mul_ptr),
+                                       int(device), vp(stream)))
 
     def info(self):
         info = tsp_projector_info()

@@ -1204,3 +1204,23 @@ extern "C" int tsp_sirt(tsp_projector *pr, void *x, const void *y, const void *R
     if (rc == TSP_OK) CUDA_TRY(cudaGetLastError());
     return rc;
 }
+
+extern "C" int tsp_project_fused(tsp_projector *pr, int direction, void *vol, void *proj, const void *sub, const void *mul,
+                                 int device, void *cuda_stream)
+{
+    if (!pr || !vol || !proj || !mul) return fail(TSP_ERR_INVALID, "NULL argument");
+    if (direction != TSP_FP && direction != TSP_BP) return fail(TSP_ERR_INVALID, "direction must be TSP_FP or TSP_BP");
+    if ((direction == TSP_FP) != (sub != nullptr))
+        return fail(TSP_ERR_INVALID, "sub is required for TSP_FP and must be NULL for TSP_BP");
+    const int ndev = tsp_device_count();
+    if (ndev == 0) return fail(TSP_ERR_CUDA, "no CUDA device available (libtsproj has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(TSP_ERR_INVALID, "device %d out of range [0, %d)", device, ndev);
+    DeviceGuard guard;
+    if (guard.enter(device) != 0) return fail(TSP_ERR_CUDA, "cannot switch to device %d", device);
+    DeviceState *st = nullptr;
+    if (int rc = get_device_state(pr, device, &st)) return rc;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    if (direction == TSP_FP)
+        return launch_fp(pr, st, (const float *)vol, (float *)proj, 0, stream, (const float *)sub, (const float *)mul);
+    return launch_bp(pr, st, (float *)vol, (const float *)proj, 0, stream, (const float *)mul);
+}
