@@ -193,7 +193,8 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
 
-    vg, pg = workload()
+    big = args.workload == "cfg4"
+    vg, pg = workload(1024, 1440) if big else workload()
     n = vg.shape[0]
     n_angles = pg.num_angles
     # N > 1: projections sharded by angle, volume sharded in z-slabs.
@@ -258,33 +259,37 @@ def run_ours(args):
     value = updates_step * args.steps / (total_ms * 1e-3) / 1e9
 
     # ---- end to end: the call a user makes, A(x) / A.T(y) on pinned HOST arrays
-    xh = torch.from_numpy(ts.phantom.hollow_box(ts.data(vg)).data).pin_memory().numpy()
-    yh = torch.empty(tuple(A.range_shape), dtype=torch.float32).pin_memory().numpy()
-    xbh = torch.empty(tuple(A.domain_shape), dtype=torch.float32).pin_memory().numpy()
-
-    def e2e_step():
-        A(xh, out=yh)
-        A.T(yh, out=xbh)
-        return float(xbh[n // 2, n // 2, n // 2])
-
-    e2e_steps = max(1, min(args.steps, 3))
-    e2e_step()
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([e2e_s], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = updates_step * e2e_steps / e2e_s / 1e9
     nvox, npix = int(np.prod(A.domain_shape)), int(np.prod(A.range_shape))
-    h2d = 4 * (nvox + npix) * world   # FP: volume in; BP: projections in
-    d2h = 4 * (npix + nvox) * world   # FP: projections out; BP: volume out
+    e2e = None
+    if not args.skip_e2e:
+        xh = torch.from_numpy(ts.phantom.hollow_box(ts.data(vg)).data).pin_memory().numpy()
+        yh = torch.empty(tuple(A.range_shape), dtype=torch.float32).pin_memory().numpy()
+        xbh = torch.empty(tuple(A.domain_shape), dtype=torch.float32).pin_memory().numpy()
+
+        def e2e_step():
+            A(xh, out=yh)
+            A.T(yh, out=xbh)
+            return float(xbh[n // 2, n // 2, n // 2])
+
+        e2e_steps = max(1, min(args.steps, 3))
+        e2e_step()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([e2e_s], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e2e_s = float(t.item())
+        e2e = {"value": updates_step * e2e_steps / e2e_s / 1e9, "unit": UNIT,
+               "h2d_bytes_per_step": 4 * (nvox + npix) * world,   # FP: volume in; BP: projections in
+               "d2h_bytes_per_step": 4 * (npix + nvox) * world,   # FP: projections out; BP: volume out
+               "steps": e2e_steps}
+        del xh, yh, xbh
 
     # ---- SIRT iterations / s on the same problem (device-resident)
     sirt_iters = max(2, min(args.steps, 5))
@@ -306,20 +311,22 @@ def run_ours(args):
         sirt_ms = e0.elapsed_time(e1) / sirt_iters
         del xs, y_tmp, R_, C_
     else:
-        from tomosipo_b200.distributed import sirt as sirt_sharded
+        from tomosipo_b200.distributed import sirt as sirt_sharded, sirt_weights
 
-        sirt_sharded(S, y, 1)
+        W_ = sirt_weights(S, dev)                       # set-up, untimed (as at N = 1)
+        xs = torch.zeros(S.slab_shape, device=dev)
+        sirt_sharded(S, y, 1, x=xs, weights=W_)
         torch.cuda.synchronize()
         dist.barrier()
         e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
         e0.record()
-        sirt_sharded(S, y, sirt_iters)
+        sirt_sharded(S, y, sirt_iters, x=xs, weights=W_)
         e1.record()
         torch.cuda.synchronize()
         t = torch.tensor([e0.elapsed_time(e1)], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        # includes the two set-up projections (R, C): count them as one extra iteration
-        sirt_ms = float(t.item()) / (sirt_iters + 1)
+        sirt_ms = float(t.item()) / sirt_iters
+        del xs, W_
 
     if rank != 0:
         if world > 1:
@@ -345,28 +352,30 @@ def run_ours(args):
         "ceiling_note": "shared-memory gather: 128 B/clk/SM / (4 taps x 4 B) (measured LDS crossbar rate, B300_MICROARCH.md)",
         "fp_kernel": fp_name, "bp_kernel": bp_name,
     }
-    t_dom = traffic.get(dom) if world == 1 else None
+    t_dom = traffic.get(dom) if world == 1 and not big else None  # the ncu capture is of cfg 3 on one GPU
     cpu_base = None
-    if world == 1:  # rank 0 at N = 1 only
+    if world == 1 and not big:  # rank 0 at N = 1 only
         cpu_gups, cpu_dt, sample = cpu_sample()
         cpu_base = {"value": cpu_gups, "unit": UNIT, "cores": omp_threads(), "kind": "port", "sample": sample}
     line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "metric": METRIC.replace("512^3 x 720", "1024^3 x 1440") if big else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cone_vec 512^3 vol, 720 angles, 512x768 det (BASELINE configs[2]), FP+BP per step",
-                   "phantom": "hollow_box", "l2": "inputs (537 MB + 1132 MB) larger than L2",
+        "config": {"workload": ("cone_vec 1024^3 vol, 1440 angles, 1024x1536 det (BASELINE configs[3]), FP+BP per step" if big else
+                                "cone_vec 512^3 vol, 720 angles, 512x768 det (BASELINE configs[2]), FP+BP per step"),
+                   "phantom": "hollow_box", "l2": ("inputs (4.3 GB + 9.1 GB) larger than L2" if big else
+                                                   "inputs (537 MB + 1132 MB) larger than L2"),
                    "parallelism": "single GPU" if world == 1 else
-                   f"angle-sharded x{world}, z-slab volume: all_gather -> FP; BP -> NCCL reduce_scatter"},
+                   f"angle-sharded x{world}, z-slab volume: NCCL all_gather -> FP; BP slab by slab -> NCCL reduce per slab (overlapped)"},
         "fp_ms": fp_ms, "bp_ms": bp_ms,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": t_dom, "peak_kind": peak_kind,
                      "algorithmic_bytes_per_launch": b_alg, "interp": interp},
         "cpu_baseline": cpu_base,
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "steps": e2e_steps},
+        "e2e": e2e,
         "sirt": {"iters_per_s": 1e3 / sirt_ms, "ms_per_iter": sirt_ms, "iterations": sirt_iters,
-                 "path": "tsp_sirt (fused epilogues)" if world == 1 else "sharded loop (all_gather / reduce_scatter)"},
+                 "path": "tsp_sirt (fused epilogues)" if world == 1 else
+                 "sharded: fused residual FP, slab-pipelined BP, per-slab NCCL reduce + broadcast on a side stream"},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
@@ -381,6 +390,9 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg4"],
+                    help="cfg3 = BASELINE configs[2] (the headline, default); cfg4 = configs[3], 1024^3 x 1440 (scaling study)")
+    ap.add_argument("--skip-e2e", action="store_true", help="leave out the host-array leg (scaling study at cfg4)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

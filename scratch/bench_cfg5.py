@@ -24,3 +24,22 @@ for _ in range(n): step()
 torch.cuda.synchronize()
 dt = (time.perf_counter() - t0) / n
 print(f"cfg5: fwd(FP,BP)+bwd(FP,BP) batch 16: {dt*1e3:.3f} ms per step = {dt*1e6/64:.1f} us per projector application; launches so far {A.astra_projector.info().kernel_launches}")
+
+# the same step captured once into a CUDA graph and replayed
+side = torch.cuda.Stream(); side.wait_stream(torch.cuda.current_stream())
+with torch.cuda.stream(side):
+    for _ in range(3):
+        x.grad = None
+        step()
+torch.cuda.current_stream().wait_stream(side)
+x.grad = None
+graph = torch.cuda.CUDAGraph()
+with torch.cuda.graph(graph):
+    step()
+for _ in range(3): graph.replay()
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(n): graph.replay()
+torch.cuda.synchronize()
+dt = (time.perf_counter() - t0) / n
+print(f"cfg5 graph replay: {dt*1e3:.3f} ms per step")

@@ -245,6 +245,33 @@ def test_stream_semantics():
 
 # ----------------------------------------------- properties at the benchmark size
 @pytest.mark.slow
+def test_device_calls_capture_into_a_cuda_graph():
+    """FP + BP on device tensors are plain stream work (kernel launches with by-value TMA descriptors,
+    stream-ordered scratch): they capture into a CUDA graph and replay on new data."""
+    vg = ts.volume(shape=(48, 64, 64), size=(0.75, 1, 1))
+    for pg in (ts.cone(angles=40, shape=(48, 96), size=(1.5, 3.0), src_orig_dist=4, src_det_dist=6),      # TMA kernels
+               ts.parallel(angles=33, shape=(2, 96), size=(2 / 48, 1.5)).to_vec()):                         # thin FP
+        A = ts.operator(vg, pg)
+        g = torch.Generator(device="cuda").manual_seed(0)
+        x = torch.rand(A.domain_shape, device="cuda", generator=g)
+        y = torch.empty(A.range_shape, device="cuda")
+        xb = torch.empty(A.domain_shape, device="cuda")
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                          # warm-up outside the capture (device tables, attributes)
+            A(x, out=y); A.T(y, out=xb)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            A(x, out=y); A.T(y, out=xb)
+        x.copy_(torch.rand(A.domain_shape, device="cuda", generator=g))
+        y.zero_(); xb.zero_()
+        graph.replay()
+        torch.cuda.synchronize()
+        y_ref = A(x)
+        assert torch.equal(y, y_ref) and torch.equal(xb, A.T(y_ref))
+
+
 def test_full_size_properties():
     n = 512
     vg = ts.volume(shape=n, size=1)

@@ -539,8 +539,9 @@ __device__ __forceinline__ void tma_load_box_3d(uint32_t dst, const void *tmap, 
 
 template <bool CONE, int ZPT>
 __global__ void __launch_bounds__(BP_TMA_THREADS, bp_tma_min_ctas(ZPT))
-bp_tma_kernel(const BPArgs P, const TensorMapBlob *__restrict__ tmap)  // tmap[0]: pitch 68 boxes, tmap[1]: pitch 60
+bp_tma_kernel(const BPArgs P, const __grid_constant__ TensorMapPair tmaps)  // m[0]: pitch 68 boxes, m[1]: pitch 60
 {
+    const TensorMapBlob *tmap = tmaps.m;
     constexpr int WV = bp_wv(ZPT);
     constexpr int STAGES = bp_tma_stages(ZPT);
     constexpr uint32_t STAGE_BYTES = (uint32_t)bp_tma_stage_bytes(ZPT);

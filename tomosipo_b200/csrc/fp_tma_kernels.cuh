@@ -177,8 +177,9 @@ __device__ __forceinline__ void fpt_consume(const FPTmaArgs &A, int kA, int kD, 
 
 template <bool CONE, bool COLS, int R>
 __global__ void __launch_bounds__(FPT_THREADS, fpt_min_ctas(R))
-fp_tma_kernel(const FPTmaArgs A, const TensorMapBlob *__restrict__ tmap)
+fp_tma_kernel(const FPTmaArgs A, const __grid_constant__ TensorMapPair tmaps)
 {
+    const TensorMapBlob *tmap = tmaps.m;
     constexpr int FPT_TV = 4 * R;
     const FPArgs &P = A.a;
     extern __shared__ __align__(128) unsigned char fpt_smem[];

@@ -51,11 +51,11 @@ struct FPGroup {
 
 // The tensor map is an opaque 128-byte, 64-byte aligned CUtensorMap.
 struct alignas(64) TensorMapBlob { unsigned char bytes[128]; };
+// The two descriptors of a launch (two box widths = two shared-memory pitches) travel as a
+// __grid_constant__ kernel parameter: no device copy to keep alive, safe under stream capture.
+struct alignas(64) TensorMapPair { TensorMapBlob m[2]; };
 
 struct DeviceState {
-    static constexpr unsigned kTmapSlots = 256;
-    TensorMapBlob *tmap_ring = nullptr;  // device copies of TMA descriptors
-    unsigned tmap_next = 0;
     FPAngle *fp_angles = nullptr;  // [n_angles], permuted per angle
     int *fp_lists = nullptr;       // concatenated group lists
     int *fp_pairs = nullptr;       // concatenated group pair lists (2 ints per pair)

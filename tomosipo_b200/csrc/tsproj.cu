@@ -331,7 +331,6 @@ static void free_device_state(tsp_projector *pr)
         cudaFree(kv.second.fp_lists);
         cudaFree(kv.second.fp_pairs);
         cudaFree(kv.second.bp_angles);
-        cudaFree(kv.second.tmap_ring);
         if (kv.second.s_in) cudaStreamDestroy(kv.second.s_in);
         if (kv.second.s_out) cudaStreamDestroy(kv.second.s_out);
     }
@@ -403,7 +402,6 @@ static int get_device_state(tsp_projector *pr, int device, DeviceState **out)
     CUDA_TRY(cudaMalloc(&st.fp_angles, A * sizeof(FPAngle)));
     CUDA_TRY(cudaMalloc(&st.bp_angles, A * sizeof(BPAngle)));
     CUDA_TRY(cudaMalloc(&st.fp_lists, A * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&st.tmap_ring, DeviceState::kTmapSlots * sizeof(TensorMapBlob)));
     CUDA_TRY(cudaMemcpy(st.fp_angles, pr->fp_angles.data(), A * sizeof(FPAngle), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMemcpy(st.bp_angles, pr->bp_angles.data(), A * sizeof(BPAngle), cudaMemcpyHostToDevice));
     std::vector<int> lists;
@@ -433,18 +431,9 @@ static int get_device_state(tsp_projector *pr, int device, DeviceState **out)
 // defined in the TMA section below
 static bool make_tensor_map_3d(const float *base, const uint64_t dims[3], const uint64_t stride_bytes[2],
                                const uint32_t box[3], TensorMapBlob *out);
-// n consecutive descriptor slots from the per-device ring (descriptors of in-flight launches are
-// never overwritten: the ring is hundreds of launches deep)
-static TensorMapBlob *tmap_slots(DeviceState *st, unsigned n)
-{
-    if (st->tmap_next + n > DeviceState::kTmapSlots) st->tmap_next = 0;
-    TensorMapBlob *p = st->tmap_ring + st->tmap_next;
-    st->tmap_next += n;
-    return p;
-}
 
 template <bool CONE, bool COLS, int R>
-static int launch_fp_tma_one(dim3 grid, size_t smem, cudaStream_t stream, const FPTmaArgs &A, const TensorMapBlob *tmap)
+static int launch_fp_tma_one(dim3 grid, size_t smem, cudaStream_t stream, const FPTmaArgs &A, const TensorMapPair &tmap)
 {
     static size_t configured[64] = {};
     int dev = 0;
@@ -548,15 +537,13 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
             if (!bw[0]) bw[0] = bw[1] ? bw[1] : grp.box_w;
             if (!bw[1]) bw[1] = bw[0];
             if (bw[0] > 256 || bw[1] > 256) bw[0] = bw[1] = grp.box_w;
-            TensorMapBlob tmap[2];
+            TensorMapPair slot;
             bool ok = true;
             for (int v = 0; v < 2 && ok; ++v) {
                 const uint32_t box[3] = {(uint32_t)bw[v], middle ? 1u : (uint32_t)grp.box_h, middle ? (uint32_t)grp.box_h : 1u};
-                ok = make_tensor_map_3d(P.vol, dims, strides, box, &tmap[v]);
+                ok = make_tensor_map_3d(P.vol, dims, strides, box, &slot.m[v]);
             }
             if (ok) {
-                TensorMapBlob *slot = tmap_slots(st, 2);
-                CUDA_TRY(cudaMemcpyAsync(slot, tmap, sizeof tmap, cudaMemcpyHostToDevice, stream));
                 FPTmaArgs T;
                 T.a = P;
                 T.pairs = st->fp_pairs + 2 * st->pair_offset[gi];
@@ -726,7 +713,7 @@ static bool make_proj_tensor_map(const float *proj, int det_u, int n_angles, int
 }
 
 template <bool CONE, int ZPT>
-static int launch_bp_tma_one(dim3 grid, cudaStream_t stream, const BPArgs &P, const TensorMapBlob *tmap)
+static int launch_bp_tma_one(dim3 grid, cudaStream_t stream, const BPArgs &P, const TensorMapPair &tmap)
 {
     static bool configured[64] = {};
     int dev = 0;
@@ -741,7 +728,7 @@ static int launch_bp_tma_one(dim3 grid, cudaStream_t stream, const BPArgs &P, co
 }
 
 static int launch_bp_tma_variant(bool cone, int zpt, dim3 grid, cudaStream_t stream, const BPArgs &P,
-                                 const TensorMapBlob *tmap)
+                                 const TensorMapPair &tmap)
 {
 #define TSP_BP_CASE(Z)                                                             \
     case Z:                                                                        \
@@ -804,18 +791,15 @@ static int launch_bp(tsp_projector *pr, DeviceState *st, float *vol, const float
         const int gy = (g.ny + BP_TY - 1) / BP_TY;
         if (gz > 65535 || gy > 65535) return fail(TSP_ERR_INVALID, "volume too large for the BP grid");
         dim3 grid((g.nx + BP_TX - 1) / BP_TX, gy, gz), block(BP_TX, BP_TY);
-        TensorMapBlob tmap[2];
+        TensorMapPair tmap;
         const bool use_tma = !getenv("TSP_BP_NO_TMA") &&
-                             make_proj_tensor_map(proj, g.det_cols, g.n_angles, g.det_rows, BP_TMA_PITCH, bp_wv(zpt), &tmap[0]) &&
-                             make_proj_tensor_map(proj, g.det_cols, g.n_angles, g.det_rows, BP_TMA_PITCH_B, bp_wv(zpt), &tmap[1]);
+                             make_proj_tensor_map(proj, g.det_cols, g.n_angles, g.det_rows, BP_TMA_PITCH, bp_wv(zpt), &tmap.m[0]) &&
+                             make_proj_tensor_map(proj, g.det_cols, g.n_angles, g.det_rows, BP_TMA_PITCH_B, bp_wv(zpt), &tmap.m[1]);
         P.magic_off = 0u - 4u * BP_MAGIC_BITS * (uint32_t)((use_tma ? BP_TMA_PITCH : BP_PITCH) + 1);
         P.magic_off_b = 0u - 4u * BP_MAGIC_BITS * (uint32_t)(BP_TMA_PITCH_B + 1);
         if (use_tma) {
-            // The descriptor lives in device memory (a small ring per device, so that
-            // back-to-back asynchronous calls never overwrite a descriptor in use).
-            TensorMapBlob *slot = tmap_slots(st, 2);
-            CUDA_TRY(cudaMemcpyAsync(slot, tmap, sizeof tmap, cudaMemcpyHostToDevice, stream));
-            if (int rc = launch_bp_tma_variant(cone, zpt, grid, stream, P, slot)) return rc;
+            // the descriptors travel as a __grid_constant__ parameter
+            if (int rc = launch_bp_tma_variant(cone, zpt, grid, stream, P, tmap)) return rc;
         } else {
             if (int rc = launch_bp_variant(cone, zpt, grid, block, stream, P)) return rc;
         }

@@ -32,6 +32,8 @@ so the next forward projection needs no all-gather.  The residual
 (``tsp_project_fused``): an iteration is one FP launch group, ``N`` BP launches
 and ``2 N`` slab-sized collectives hidden behind them.
 """
+import os
+
 import numpy as np
 import torch
 import torch.distributed as dist
@@ -80,7 +82,9 @@ class ShardedOperator:
         self._transpose = _ShardedTranspose(self)
         # z-slab sub-operators of the pipelined backprojection (built on first use)
         self._make_local = make_local or ts.operator
-        self.pipeline = (self.world > 1) if pipeline is None else (bool(pipeline) and self.world > 1)
+        if pipeline is None:  # TSP_SHARD_NO_PIPELINE: measurement aid (one reduce_scatter / all_gather per call)
+            pipeline = not os.environ.get("TSP_SHARD_NO_PIPELINE")
+        self.pipeline = bool(pipeline) and self.world > 1
         self._slab_ops = None
         self._comm_stream = None
 
@@ -259,25 +263,35 @@ class _ShardedTranspose:
         return self.parent
 
 
-def sirt(A, y, num_iterations, x=None, eps=None):
-    """SIRT with the volume sharded in z (loop of ``notebooks/sirt_benchmark.py:116-139``).
-
-    ``A`` is a :class:`ShardedOperator` (or any operator with the same call
-    signature), ``y`` this rank's angle block.  Returns this rank's padded
-    z-slab of the reconstruction.
-    """
+def sirt_weights(A, device, eps=None):
+    """``(R, C)`` = ``(1 / A(1), 1 / A.T(1))`` clamped like ``notebooks/sirt_benchmark.py:116-128``:
+    ``R`` for this rank's angle block, ``C`` for its z-slab."""
     eps = ts.epsilon if eps is None else eps
-    dev = y.device
-    y_tmp = torch.ones(A.proj_shape, device=dev)
+    y_tmp = torch.ones(A.proj_shape, device=device)
     C = A.T(y_tmp)
     C[C < eps] = float("inf")
     C.reciprocal_()
-    x_tmp = torch.ones(A.slab_shape, device=dev)
+    x_tmp = torch.ones(A.slab_shape, device=device)
     if A.z_hi - A.z_lo < A.slab_nz:
         x_tmp[A.z_hi - A.z_lo:] = 0  # padding rows stay empty
     R = A(x_tmp)
     R[R < eps] = float("inf")
     R.reciprocal_()
+    return R, C
+
+
+def sirt(A, y, num_iterations, x=None, eps=None, weights=None):
+    """SIRT with the volume sharded in z (loop of ``notebooks/sirt_benchmark.py:116-139``).
+
+    ``A`` is a :class:`ShardedOperator` (or any operator with the same call
+    signature), ``y`` this rank's angle block, ``weights`` an optional
+    ``(R, C)`` from :func:`sirt_weights`.  Returns this rank's padded z-slab of
+    the reconstruction.
+    """
+    dev = y.device
+    R, C = sirt_weights(A, dev, eps) if weights is None else weights
+    y_tmp = torch.empty(A.proj_shape, device=dev)
+    x_tmp = torch.empty(A.slab_shape, device=dev)
     x_cur = torch.zeros(A.slab_shape, device=dev) if x is None else x
     if getattr(A, "pipeline", False):
         return _sirt_pipelined(A, y, R, C, x_cur, y_tmp, num_iterations)
