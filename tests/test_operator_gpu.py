@@ -200,6 +200,12 @@ def test_autograd_extra_dims_match_loop(extra):
     with pytest.warns(UserWarning):
         yt = f(xt)
     assert torch.allclose(yt, f(xt.contiguous()))
+    # the expanded (stride-0) gradient of a sum takes the batched path after one copy
+    xg = torch.rand(*extra, 12, 12, device="cuda", requires_grad=True)
+    with pytest.warns(UserWarning):
+        f(xg).sum().backward()
+    g_ref = to_autograd(A.T, num_extra_dims=len(extra), is_2d=True)(torch.ones_like(f(xg.detach())))
+    assert torch.allclose(xg.grad, g_ref)
 
 
 def test_autograd_operator():

@@ -455,7 +455,7 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
     const size_t npix = (size_t)g.det_rows * g.n_angles * g.det_cols;
     // thin detectors (cfg 5 slabs): one launch per angle group covers the whole batch (thin_kernels.cuh)
     const bool thin = g.det_rows <= THIN_MAX && g.detector_supersampling == 1 && !getenv("TSP_NO_THIN") &&
-                      (long long)batch * g.det_rows <= 65535;
+                      (long long)batch * g.det_rows <= 65535 && (size_t)batch * std::max(nvox, npix) < (1ull << 40);
     if (!thin && batch > 1) {
         for (int b = 0; b < batch; ++b)
             if (int rc = launch_fp(pr, st, vol + b * nvox, proj + b * npix, additive, stream,
@@ -508,11 +508,16 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
             P.det_ss = 1;
             const int na = (int)grp.angles.size();
             if ((na + THIN_FP_ANGLES - 1) / THIN_FP_ANGLES > 65535) return fail(TSP_ERR_INVALID, "too many angles for the thin FP grid");
-            dim3 tgrid((g.det_cols + 31) / 32, (na + THIN_FP_ANGLES - 1) / THIN_FP_ANGLES, batch * g.det_rows);
+            const int bt = batch >= THIN_BT ? THIN_BT : 1;  // batch items per thread
+            const int groups = (batch + bt - 1) / bt;
+            dim3 tgrid((g.det_cols + 31) / 32, (na + THIN_FP_ANGLES - 1) / THIN_FP_ANGLES, groups * g.det_rows);
             dim3 tblock(32, THIN_FP_ANGLES);
             const size_t vstride = grp.transposed ? (size_t)g.nz * g.nx * ny_pad : nvox;
-            if (cone) fp_thin_kernel<true><<<tgrid, tblock, 0, stream>>>(P, na, vstride, npix);
-            else fp_thin_kernel<false><<<tgrid, tblock, 0, stream>>>(P, na, vstride, npix);
+#define TSP_THIN_FP(C) (bt == 1 ? fp_thin_kernel<C, 1><<<tgrid, tblock, 0, stream>>>(P, na, batch, vstride, npix) \
+                                : fp_thin_kernel<C, THIN_BT><<<tgrid, tblock, 0, stream>>>(P, na, batch, vstride, npix))
+            if (cone) TSP_THIN_FP(true);
+            else TSP_THIN_FP(false);
+#undef TSP_THIN_FP
             ++pr->launches;
             continue;
         }
@@ -777,9 +782,13 @@ static int launch_bp(tsp_projector *pr, DeviceState *st, float *vol, const float
     if (thin) {
         const int gy = (g.ny + BP_TY - 1) / BP_TY;
         if (gy > 65535) return fail(TSP_ERR_INVALID, "volume too large for the BP grid");
-        dim3 grid((g.nx + BP_TX - 1) / BP_TX, gy, batch), block(BP_TX, BP_TY);
-        if (cone) bp_thin_kernel<true><<<grid, block, 0, stream>>>(P, nvox_b, npix_b);
-        else bp_thin_kernel<false><<<grid, block, 0, stream>>>(P, nvox_b, npix_b);
+        const int bt = batch >= THIN_BT ? THIN_BT : 1;  // batch items per thread
+        dim3 grid((g.nx + BP_TX - 1) / BP_TX, gy, (batch + bt - 1) / bt), block(BP_TX, BP_TY);
+#define TSP_THIN_BP(C) (bt == 1 ? bp_thin_kernel<C, 1><<<grid, block, 0, stream>>>(P, batch, nvox_b, npix_b) \
+                                : bp_thin_kernel<C, THIN_BT><<<grid, block, 0, stream>>>(P, batch, nvox_b, npix_b))
+        if (cone) TSP_THIN_BP(true);
+        else TSP_THIN_BP(false);
+#undef TSP_THIN_BP
     } else if (g.voxel_supersampling > 1) {
         if (g.nz > 65535) return fail(TSP_ERR_INVALID, "voxel supersampling supports nz <= 65535");
         dim3 grid((g.nx + 31) / 32, (g.ny + 7) / 8, g.nz), block(32, 8);

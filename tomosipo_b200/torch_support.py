@@ -44,6 +44,16 @@ def _project_batched(operator, src, dst, extra_dims):
     base = operator.parent if isinstance(operator, BackprojectionOperator) else operator
     forward = not isinstance(operator, BackprojectionOperator)
     n = math.prod(extra_dims)
+    if (isinstance(base, Operator) and not base.additive and n > 0 and src.dtype == torch.float32
+            and not src.is_contiguous() and dst.is_contiguous()):
+        # e.g. the expanded gradient of a sum: one copy of the batch (with the link's warning, once)
+        # instead of one copy + one projector call per sub-tensor
+        warnings.warn(
+            "The parameter initial_value should be contiguous. "
+            "It has been automatically made contiguous. "
+            "Use `ts.link(x.contiguous())' to inhibit this warning. "
+        )
+        src = src.contiguous()
     dense = (
         isinstance(base, Operator)
         and not base.additive
