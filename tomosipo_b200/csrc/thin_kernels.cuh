@@ -19,8 +19,20 @@ constexpr int THIN_BT = 4;          // batch items per thread in the batched ins
 // All items of a batch share the geometry: a thread computes the tap offsets and weights of a
 // sample once and applies them to BT batch items (BT = 1 or THIN_BT), so the index arithmetic --
 // most of the instructions of a bounds-checked bilinear gather -- is amortised over the batch.
-// Out-of-volume taps get weight 0 and a clamped (valid) offset; a row of taps whose weight is 0
-// (always the case for one of the two rows of a single-slice slab) is skipped.
+// Border rule without branches: the 2 x 2 tap window is shifted into the array
+// (c = clamp(i, 0, n - 2)) and the two weights are re-assigned to the shifted positions, taps that
+// fall outside get weight 0.  Needs n >= 2 along the contiguous axis (the host checks); an axis of
+// length 1 (the single slice of a slab) has one row and one weight.
+
+// Weights of the array elements c and c + 1 for a sample at index coordinate f, where
+// c = clamp(floor(f), 0, n - 2): linear interpolation with zeros outside the array is the hat
+// function max(0, 1 - |f - j|) of every element j, so the shifted window needs no case analysis.
+__device__ __forceinline__ void thin_hat_weights(float f, int c, float &w0, float &w1)
+{
+    const float x = f - (float)c;
+    w0 = fmaxf(0.0f, 1.0f - fabsf(x));
+    w1 = fmaxf(0.0f, 1.0f - fabsf(x - 1.0f));
+}
 
 // grid: (det_u tiles of 32, angle tiles of 8, batch groups * det_v)
 template <bool CONE, int BT>
@@ -29,9 +41,11 @@ __global__ void __launch_bounds__(32 * THIN_FP_ANGLES) fp_thin_kernel(const FPAr
 {
     const int bg = blockIdx.z / P.det_v, iv = blockIdx.z % P.det_v;
     const int b0 = bg * BT;
+    const int nb = min(BT, batch - b0);
     const int ai = blockIdx.y * THIN_FP_ANGLES + threadIdx.y;
     const int iu = blockIdx.x * 32 + threadIdx.x;
-    if (ai >= n_list || iu >= P.det_u) return;
+    if (ai >= n_list) return;  // warp-uniform (threadIdx.y is the warp)
+    const bool live = iu < P.det_u;
     const int a = P.list[ai];
     const FPAngle g = P.angles[a];
     const double cu = (double)iu + 0.5, cv = (double)iv + 0.5;
@@ -51,39 +65,53 @@ __global__ void __launch_bounds__(32 * THIN_FP_ANGLES) fp_thin_kernel(const FPAr
     float f1, l1, f2, l2;
     k_interval(ap, cp, t0, -1.0f, (float)P.n_p, f1, l1);
     k_interval(aq, cq, t0, -1.0f, (float)P.n_q, f2, l2);
-    const int k_lo = clamp_f2i(fmaxf(f1, f2) - 1.0f, 0, P.n_m, false);
-    const int k_hi = clamp_f2i(fminf(l1, l2) + 1.0f, 0, P.n_m, true);  // exclusive
+    int k_lo = clamp_f2i(fmaxf(f1, f2) - 1.0f, 0, P.n_m, false);
+    int k_hi = clamp_f2i(fminf(l1, l2) + 1.0f, 0, P.n_m, true);  // exclusive
+    if (!live) { k_lo = P.n_m; k_hi = 0; }
+    // the warp walks the slices together (its lanes read neighbouring voxels of one slice: coalesced);
+    // outside its own interval a lane's taps are outside the volume and weigh 0
+    const int kA = warp_min_i(k_lo), kD = warp_max_i(k_hi);
 
+    // 32-bit element offsets (the host takes this path only when a whole batch has < 2^31 elements)
     float acc[BT];
+    uint32_t ob[BT];
+    const float *vol0 = P.vol + (size_t)b0 * vol_bstride;
+    asm volatile("" : "+l"(vol0));  // keep the base in a register pair (ptxas otherwise re-derives it per load)
 #pragma unroll
-    for (int j = 0; j < BT; ++j) acc[j] = 0.0f;
-    const float *__restrict__ vol = P.vol + (size_t)b0 * vol_bstride;
-    const int nb = min(BT, batch - b0);
-    for (int k = k_lo; k < k_hi; ++k) {
+    for (int j = 0; j < BT; ++j) {
+        acc[j] = 0.0f;
+        ob[j] = (uint32_t)min(j, nb - 1) * (uint32_t)vol_bstride;  // surplus items of the last group repeat a valid one
+        asm volatile("" : "+r"(ob[j]));
+    }
+    const uint32_t sm32 = (uint32_t)P.stride_m, sq32 = (uint32_t)P.stride_q;
+    const bool one_row = P.n_q < 2;
+    const int rmax = max(P.n_q - 2, 0);
+    for (int k = kA; k < kD; ++k) {
         const float t = (float)k + t0;
-        const float fp = fmaf(ap, t, cp), fq = fmaf(aq, t, cq);
-        const float flp = floorf(fp), flq = floorf(fq);
-        const int ip = (int)flp, iq = (int)flq;
-        const float wp = fp - flp, wq = fq - flq;
-        const float wp0 = (ip >= 0 && ip < P.n_p) ? 1.0f - wp : 0.0f, wp1 = (ip >= -1 && ip + 1 < P.n_p) ? wp : 0.0f;
-        const float wq0 = (iq >= 0 && iq < P.n_q) ? 1.0f - wq : 0.0f, wq1 = (iq >= -1 && iq + 1 < P.n_q) ? wq : 0.0f;
-        const int c0 = min(max(ip, 0), P.n_p - 1), c1 = min(max(ip + 1, 0), P.n_p - 1);
-        const int r0 = min(max(iq, 0), P.n_q - 1), r1 = min(max(iq + 1, 0), P.n_q - 1);
-        const float *s0 = vol + (long long)k * P.stride_m + (long long)r0 * P.stride_q;
-        const float *s1 = vol + (long long)k * P.stride_m + (long long)r1 * P.stride_q;
-        if (wq0 != 0.0f) {
-            const float w0 = wq0 * wp0, w1 = wq0 * wp1;
+        const float fp = fmaf(ap, t, cp), fq = fmaf(aq, t, cq);  // (float -> int saturates; far-away samples weigh 0)
+        const int c = min(max(__float2int_rd(fp), 0), P.n_p - 2);
+        const int r = min(max(__float2int_rd(fq), 0), rmax);
+        float wp0, wp1, wq0, wq1;
+        thin_hat_weights(fp, c, wp0, wp1);
+        thin_hat_weights(fq, r, wq0, wq1);
+        if (one_row) wq1 = 0.0f;
+        const uint32_t off = (uint32_t)k * sm32 + (uint32_t)r * sq32 + (uint32_t)c;
+        const float w00 = wq0 * wp0, w01 = wq0 * wp1;
 #pragma unroll
-            for (int j = 0; j < BT; ++j)
-                if (j < nb) acc[j] = fmaf(w0, __ldg(s0 + j * vol_bstride + c0), fmaf(w1, __ldg(s0 + j * vol_bstride + c1), acc[j]));
+        for (int j = 0; j < BT; ++j) {
+            const float *s = vol0 + (ob[j] + off);
+            acc[j] = fmaf(w00, __ldg(s), fmaf(w01, __ldg(s + 1), acc[j]));
         }
         if (wq1 != 0.0f) {
-            const float w0 = wq1 * wp0, w1 = wq1 * wp1;
+            const float w10 = wq1 * wp0, w11 = wq1 * wp1;
 #pragma unroll
-            for (int j = 0; j < BT; ++j)
-                if (j < nb) acc[j] = fmaf(w0, __ldg(s1 + j * vol_bstride + c0), fmaf(w1, __ldg(s1 + j * vol_bstride + c1), acc[j]));
+            for (int j = 0; j < BT; ++j) {
+                const float *s = vol0 + (ob[j] + off + sq32);
+                acc[j] = fmaf(w10, __ldg(s), fmaf(w11, __ldg(s + 1), acc[j]));
+            }
         }
     }
+    if (!live) return;
     const size_t pix = ((size_t)iv * P.n_angles + a) * P.det_u + iu;
 #pragma unroll
     for (int j = 0; j < BT; ++j)
@@ -104,7 +132,6 @@ __global__ void __launch_bounds__(BP_THREADS) bp_thin_kernel(const BPArgs P, int
     __shared__ float loc[THIN_BP_BATCH][16];  // au[3] bu | av[3] bv | ad[3] bd | weight
     const int b0 = blockIdx.z * BT;
     const int nb = min(BT, batch - b0);
-    const float *__restrict__ proj = P.proj + (size_t)b0 * proj_bstride;
     const int tx = threadIdx.x, ty = threadIdx.y, tid = ty * BP_TX + tx;
     const int x0 = blockIdx.x * BP_TX, y0 = blockIdx.y * BP_TY;
     const int x1 = min(x0 + BP_TX, P.nx) - 1, y1 = min(y0 + BP_TY, P.ny) - 1;
@@ -118,12 +145,22 @@ __global__ void __launch_bounds__(BP_THREADS) bp_thin_kernel(const BPArgs P, int
     const float dz0 = (float)(0.5 - 0.5 * P.nz);
     const bool in_xy = (x < P.nx) && (y < P.ny);
     const size_t row_pitch = (size_t)P.n_angles * P.det_u;
+    const bool one_row = P.det_v < 2;
+    const int rmax = max(P.det_v - 2, 0);
 
+    // 32-bit element offsets (the host takes this path only when a whole batch has < 2^31 elements)
     float acc[THIN_MAX][BT];
+    uint32_t ob[BT];
+    const float *proj0 = P.proj + (size_t)b0 * proj_bstride;
+    asm volatile("" : "+l"(proj0));  // keep the base in a register pair (ptxas otherwise re-derives it per load)
+    const uint32_t rp32 = (uint32_t)row_pitch;
 #pragma unroll
-    for (int i = 0; i < THIN_MAX; ++i)
+    for (int b = 0; b < BT; ++b) {
+        ob[b] = (uint32_t)min(b, nb - 1) * (uint32_t)proj_bstride;  // surplus items repeat a valid one
+        asm volatile("" : "+r"(ob[b]));
 #pragma unroll
-        for (int j = 0; j < BT; ++j) acc[i][j] = 0.0f;
+        for (int i = 0; i < THIN_MAX; ++i) acc[i][b] = 0.0f;
+    }
 
     for (int a0 = 0; a0 < P.n_angles; a0 += THIN_BP_BATCH) {
         const int na = min(THIN_BP_BATCH, P.n_angles - a0);
@@ -153,7 +190,7 @@ __global__ void __launch_bounds__(BP_THREADS) bp_thin_kernel(const BPArgs P, int
             float nu = fmaf(L[0], dx, fmaf(L[1], dy, fmaf(L[2], dz0, L[3])));
             float nv = fmaf(L[4], dx, fmaf(L[5], dy, fmaf(L[6], dz0, L[7])));
             float dn = CONE ? fmaf(L[8], dx, fmaf(L[9], dy, fmaf(L[10], dz0, L[11]))) : 1.0f;
-            const float *src = proj + (size_t)(a0 + j) * P.det_u;
+            const uint32_t aoff = (uint32_t)(a0 + j) * (uint32_t)P.det_u;
 #pragma unroll
             for (int i = 0; i < THIN_MAX; ++i) {
                 if (i < P.nz) {
@@ -164,30 +201,27 @@ __global__ void __launch_bounds__(BP_THREADS) bp_thin_kernel(const BPArgs P, int
                     } else {
                         fu = nu; fv = nv; w2 = L[12];
                     }
-                    if (fu > -1.0f && fu < (float)P.det_u && fv > -1.0f && fv < (float)P.det_v) {
-                        const float flu = floorf(fu), flv = floorf(fv);
-                        const int iu = (int)flu, iv = (int)flv;
-                        const float wu = fu - flu, wv = fv - flv;
-                        const float wu0 = iu >= 0 ? 1.0f - wu : 0.0f, wu1 = iu + 1 < P.det_u ? wu : 0.0f;
-                        const float wv0 = (iv >= 0 ? 1.0f - wv : 0.0f) * w2, wv1 = (iv + 1 < P.det_v ? wv : 0.0f) * w2;
-                        const int c0 = max(iu, 0), c1 = min(iu + 1, P.det_u - 1);
-                        const float *s0 = src + (size_t)max(iv, 0) * row_pitch;
-                        const float *s1 = src + (size_t)min(iv + 1, P.det_v - 1) * row_pitch;
-                        if (wv0 != 0.0f) {
-                            const float w0 = wv0 * wu0, w1 = wv0 * wu1;
+                    // (float -> int saturates; far-away samples weigh 0)
+                    const int c = min(max(__float2int_rd(fu), 0), P.det_u - 2);
+                    const int r = min(max(__float2int_rd(fv), 0), rmax);
+                    float wu0, wu1, wv0, wv1;
+                    thin_hat_weights(fu, c, wu0, wu1);
+                    thin_hat_weights(fv, r, wv0, wv1);
+                    if (one_row) wv1 = 0.0f;
+                    wv0 *= w2; wv1 *= w2;
+                    const uint32_t off = aoff + (uint32_t)r * rp32 + (uint32_t)c;
+                    const float w00 = wv0 * wu0, w01 = wv0 * wu1;
 #pragma unroll
-                            for (int b = 0; b < BT; ++b)
-                                if (b < nb)
-                                    acc[i][b] = fmaf(w0, __ldg(s0 + b * proj_bstride + c0),
-                                                     fmaf(w1, __ldg(s0 + b * proj_bstride + c1), acc[i][b]));
-                        }
-                        if (wv1 != 0.0f) {
-                            const float w0 = wv1 * wu0, w1 = wv1 * wu1;
+                    for (int b = 0; b < BT; ++b) {
+                        const float *s = proj0 + (ob[b] + off);
+                        acc[i][b] = fmaf(w00, __ldg(s), fmaf(w01, __ldg(s + 1), acc[i][b]));
+                    }
+                    if (wv1 != 0.0f) {
+                        const float w10 = wv1 * wu0, w11 = wv1 * wu1;
 #pragma unroll
-                            for (int b = 0; b < BT; ++b)
-                                if (b < nb)
-                                    acc[i][b] = fmaf(w0, __ldg(s1 + b * proj_bstride + c0),
-                                                     fmaf(w1, __ldg(s1 + b * proj_bstride + c1), acc[i][b]));
+                        for (int b = 0; b < BT; ++b) {
+                            const float *s = proj0 + (ob[b] + off + rp32);
+                            acc[i][b] = fmaf(w10, __ldg(s), fmaf(w11, __ldg(s + 1), acc[i][b]));
                         }
                     }
                     nu += L[2]; nv += L[6];

@@ -455,7 +455,9 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
     const size_t npix = (size_t)g.det_rows * g.n_angles * g.det_cols;
     // thin detectors (cfg 5 slabs): one launch per angle group covers the whole batch (thin_kernels.cuh)
     const bool thin = g.det_rows <= THIN_MAX && g.detector_supersampling == 1 && !getenv("TSP_NO_THIN") &&
-                      (long long)batch * g.det_rows <= 65535 && (size_t)batch * std::max(nvox, npix) < (1ull << 40);
+                      (long long)batch * g.det_rows <= 65535 && (size_t)batch * g.nz * (g.nx + 4) * (g.ny + 4) < (1ull << 31) &&  // 32-bit offsets, either layout
+                     
+                      g.nx >= 2 && g.ny >= 2;  // the thin kernels shift their tap window into the array
     if (!thin && batch > 1) {
         for (int b = 0; b < batch; ++b)
             if (int rc = launch_fp(pr, st, vol + b * nvox, proj + b * npix, additive, stream,
@@ -757,7 +759,9 @@ static int launch_bp(tsp_projector *pr, DeviceState *st, float *vol, const float
     const size_t nvox_b = (size_t)g.nx * g.ny * g.nz;
     const size_t npix_b = (size_t)g.det_rows * g.n_angles * g.det_cols;
     // thin volumes (cfg 5 slabs): one launch covers the whole batch (thin_kernels.cuh)
-    const bool thin = g.nz <= THIN_MAX && g.voxel_supersampling == 1 && !getenv("TSP_NO_THIN") && batch <= 65535;
+    const bool thin = g.nz <= THIN_MAX && g.voxel_supersampling == 1 && !getenv("TSP_NO_THIN") && batch <= 65535 &&
+                      (size_t)batch * npix_b < (1ull << 31) &&  // 32-bit offsets
+                      g.det_cols >= 2;  // the thin kernels shift their tap window into the array
     if (!thin && batch > 1) {
         for (int b = 0; b < batch; ++b)
             if (int rc = launch_bp(pr, st, vol + b * nvox_b, proj + b * npix_b, additive, stream,
