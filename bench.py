@@ -366,7 +366,7 @@ def run_ours(args):
                    "phantom": "hollow_box", "l2": ("inputs (4.3 GB + 9.1 GB) larger than L2" if big else
                                                    "inputs (537 MB + 1132 MB) larger than L2"),
                    "parallelism": "single GPU" if world == 1 else
-                   f"angle-sharded x{world}, z-slab volume: NCCL all_gather -> FP; BP slab by slab -> NCCL reduce per slab (overlapped)"},
+                   f"angle-sharded x{world}, z-sharded volume: NCCL all_gather -> FP; BP in {S.chunks} z-chunks -> NCCL reduce_scatter per chunk (overlapped)"},
         "fp_ms": fp_ms, "bp_ms": bp_ms,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": t_dom, "peak_kind": peak_kind,
@@ -375,7 +375,8 @@ def run_ours(args):
         "e2e": e2e,
         "sirt": {"iters_per_s": 1e3 / sirt_ms, "ms_per_iter": sirt_ms, "iterations": sirt_iters,
                  "path": "tsp_sirt (fused epilogues)" if world == 1 else
-                 "sharded: fused residual FP, slab-pipelined BP, per-slab NCCL reduce + broadcast on a side stream"},
+                 f"sharded: fused residual FP; BP in {S.chunks} z-chunks, each chunk's NCCL reduce_scatter + update + "
+                 "all_gather on a side stream behind the next chunk's kernel"},
         "gpu_launches": int(launches),
         "clocks": clocks,
     }

@@ -59,31 +59,38 @@ def _worker(rank, world, port, tmpdir):
     try:
         torch.manual_seed(0)
         vg, pg = geometries()
-        S = ShardedOperator(vg, pg, make_local=OracleOperator)
         ref = OracleOperator(vg, pg)
         x = torch.rand(vg.shape)
         y_full = ref(x)
-        # forward: own angle block of the full projection
-        y_blk = S(S.scatter_volume(x))
-        lo, hi = shard_bounds(pg.num_angles, world, rank)
-        assert (S.angle_lo, S.angle_hi) == (lo, hi)
-        torch.testing.assert_close(y_blk, y_full[:, lo:hi, :], rtol=1e-5, atol=1e-6)
-        # backward: own z-slab of the full backprojection
         w = torch.rand(y_full.shape)
-        slab = S.T(w[:, lo:hi, :].contiguous())
         full_bp = ref.T(w)
-        torch.testing.assert_close(slab[: S.z_hi - S.z_lo], full_bp[S.z_lo:S.z_hi], rtol=1e-4, atol=1e-5)
-        assert float(slab[S.z_hi - S.z_lo:].abs().sum()) == 0.0            # padding stays empty
-        torch.testing.assert_close(S.gather_volume(slab), full_bp, rtol=1e-4, atol=1e-5)
-        # the slab-pipelined exchange (default for world > 1) against one reduce_scatter per call
-        S1 = ShardedOperator(vg, pg, make_local=OracleOperator, pipeline=False)
-        assert S.pipeline and not S1.pipeline
-        assert [(j, a, b) for j, a, b, _ in S.slab_operators()] == [(0, 0, 5), (1, 5, 9)]
-        torch.testing.assert_close(S1.T(w[:, lo:hi, :].contiguous()), slab, rtol=1e-5, atol=1e-6)
-        rec1 = S1.gather_volume(sirt(S1, y_full[:, lo:hi, :].contiguous(), 4))
-        # SIRT: sharded == single-process
-        rec = S.gather_volume(sirt(S, y_full[:, lo:hi, :].contiguous(), 4))
-        torch.testing.assert_close(rec, rec1, rtol=1e-4, atol=1e-5)
+        lo, hi = shard_bounds(pg.num_angles, world, rank)
+        recs = []
+        # chunks = 1: contiguous slabs, one collective per call; chunks = 2: interleaved pieces, the
+        # overlapped exchange (9 slices over 2 x 2 pieces of 3: the last piece is all padding)
+        for chunks in (1, 2):
+            S = ShardedOperator(vg, pg, make_local=OracleOperator, chunks=chunks)
+            assert (S.angle_lo, S.angle_hi) == (lo, hi) and S.chunks == chunks
+            if chunks == 1:
+                assert (S.z_lo, S.z_hi) == ((0, 5) if rank == 0 else (5, 9)) and S.slab_geometry().shape[0] == S.z_hi - S.z_lo
+            else:
+                assert S.slab_pieces() == ([(0, 0, 3), (3, 6, 9)] if rank == 0 else [(0, 3, 6), (3, 9, 9)])
+                with pytest.raises(ValueError):
+                    S.slab_geometry()
+            # forward: own angle block of the full projection
+            y_blk = S(S.scatter_volume(x))
+            torch.testing.assert_close(y_blk, y_full[:, lo:hi, :], rtol=1e-5, atol=1e-6)
+            # backward: own pieces of the full backprojection, padding rows stay empty
+            slab = S.T(w[:, lo:hi, :].contiguous())
+            for row, z0, z1 in S.slab_pieces():
+                torch.testing.assert_close(slab[row: row + z1 - z0], full_bp[z0:z1], rtol=1e-4, atol=1e-5)
+                assert float(slab[row + z1 - z0: row + S.piece_nz].abs().sum()) == 0.0
+            torch.testing.assert_close(S.gather_volume(slab), full_bp, rtol=1e-4, atol=1e-5)
+            torch.testing.assert_close(S.gather_volume(S.scatter_volume(x)), x)
+            # SIRT: sharded == single-process (compared below), both layouts agree
+            recs.append(S.gather_volume(sirt(S, y_full[:, lo:hi, :].contiguous(), 4)))
+        torch.testing.assert_close(recs[0], recs[1], rtol=1e-4, atol=1e-5)
+        rec = recs[1]
         torch.save(rec, os.path.join(tmpdir, f"rec{rank}.pt"))
         with pytest.raises(ValueError):
             S(torch.zeros(3, 3, 3))
@@ -105,7 +112,7 @@ def test_sharded_operator_and_sirt_two_ranks(tmp_path):
     x = torch.rand(vg.shape)
 
     class Single:
-        proj_shape, slab_shape, slab_nz, z_lo, z_hi = tuple(ref(x).shape), vg.shape, vg.shape[0], 0, vg.shape[0]
+        proj_shape, slab_shape = tuple(ref(x).shape), vg.shape
         T = ref.T
 
         def __call__(self, v, out=None):
@@ -126,7 +133,7 @@ def test_shard_bounds_cover_everything():
 def test_single_process_sharded_operator_is_identity_wrapper():
     vg, pg = geometries()
     S = ShardedOperator(vg, pg, make_local=OracleOperator)
-    assert S.world == 1 and S.slab_shape == vg.shape and S.T.T is S
+    assert S.world == 1 and S.chunks == 1 and S.slab_shape == vg.shape and S.T.T is S
     x = torch.rand(vg.shape)
     torch.testing.assert_close(S(x), OracleOperator(vg, pg)(x))
     with pytest.raises(TypeError):

@@ -22,37 +22,37 @@ def _worker(rank, world, port, tmpdir):
     try:
         vg = ts.volume(shape=(50, 48, 56), size=(1.0, 0.96, 1.12))      # 50 slices: padded slabs for world = 4
         pg = ts.cone(angles=37, shape=(40, 64), size=(2.0, 3.2), src_orig_dist=4, src_det_dist=7)
-        S = ShardedOperator(vg, pg)
         A = ts.operator(vg, pg)
         g = torch.Generator(device="cuda").manual_seed(0)
         x = torch.rand(vg.shape, device="cuda", generator=g)
         w = torch.rand(A.range_shape, device="cuda", generator=g)
+        Rw = torch.rand(A.range_shape, device="cuda", generator=g)
         y_full, bp_full = A(x), A.T(w)
-        y_blk = S(S.scatter_volume(x))
-        assert torch.equal(y_blk, y_full[:, S.angle_lo:S.angle_hi, :])      # FP per angle is independent: bit-exact
-        slab = S.T(w[:, S.angle_lo:S.angle_hi, :].contiguous())
-        torch.testing.assert_close(S.gather_volume(slab), bp_full, rtol=1e-5, atol=1e-6)   # sum order differs
-        # slab-pipelined exchange (default) against one reduce_scatter per call
-        S1 = ShardedOperator(vg, pg, pipeline=False)
-        assert S.pipeline and not S1.pipeline
-        slab1 = S1.T(w[:, S.angle_lo:S.angle_hi, :].contiguous())
-        torch.testing.assert_close(slab1, slab, rtol=1e-5, atol=1e-6)
-        rec1 = S1.gather_volume(sirt(S1, y_full[:, S.angle_lo:S.angle_hi, :].contiguous(), 5))
-        rec = S.gather_volume(sirt(S, y_full[:, S.angle_lo:S.angle_hi, :].contiguous(), 5))
-        assert float(torch.linalg.vector_norm(rec - rec1) / torch.linalg.vector_norm(rec1)) < 1e-5
-        # fused residual == explicit three passes
-        xf = x.contiguous()
-        yb = y_full[:, S.angle_lo:S.angle_hi, :].contiguous()
-        Rw = torch.rand(S.proj_shape, device="cuda", generator=g)
-        r_fused = S.residual(xf, yb, Rw, torch.empty_like(yb))
-        torch.testing.assert_close(r_fused, Rw * (S.local(xf) - yb), rtol=1e-5, atol=1e-6)
+        recs = []
+        # chunks = 1: contiguous slabs, one collective per call; chunks = 3: interleaved pieces with the
+        # exchange overlapped chunk by chunk on a second stream (50 slices: padded pieces)
+        for chunks in (1, 3):
+            S = ShardedOperator(vg, pg, chunks=chunks)
+            blk = slice(S.angle_lo, S.angle_hi)
+            y_blk = S(S.scatter_volume(x))
+            assert torch.equal(y_blk, y_full[:, blk, :])                    # FP per angle is independent: bit-exact
+            slab = S.T(w[:, blk, :].contiguous())
+            torch.testing.assert_close(S.gather_volume(slab), bp_full, rtol=1e-5, atol=1e-6)   # sum order differs
+            for row, z0, z1 in S.slab_pieces():
+                assert float(slab[row + z1 - z0: row + S.piece_nz].abs().sum()) == 0.0          # padding stays empty
+            # fused residual == explicit three passes
+            yb, Rb = y_full[:, blk, :].contiguous(), Rw[:, blk, :].contiguous()
+            r_fused = S.residual(x.contiguous(), yb, Rb, torch.empty_like(yb))
+            torch.testing.assert_close(r_fused, Rb * (S.local(x) - yb), rtol=1e-5, atol=1e-6)
+            recs.append(S.gather_volume(sirt(S, yb, 5)))
+        assert float(torch.linalg.vector_norm(recs[0] - recs[1]) / torch.linalg.vector_norm(recs[0])) < 1e-5
+        rec = recs[1]
         if rank == 0:
             torch.save(rec.cpu(), os.path.join(tmpdir, "rec.pt"))
             # single-GPU SIRT with the same loop
 
             class Single:
                 proj_shape, slab_shape = tuple(A.range_shape), tuple(vg.shape)
-                slab_nz, z_lo, z_hi = vg.shape[0], 0, vg.shape[0]
                 T = A.T
 
                 def __call__(self, v, out=None):

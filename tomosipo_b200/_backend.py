@@ -13,7 +13,8 @@ import threading
 import numpy as np
 
 _PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG_DIR, "libtsproj.so")
+# TSPROJ_LIB: load another build of the same sources (kernel tuning experiments)
+LIB_PATH = os.environ.get("TSPROJ_LIB") or os.path.join(_PKG_DIR, "libtsproj.so")
 CSRC_DIR = os.path.join(_PKG_DIR, "csrc")
 
 KIND_CONE_VEC = 0

@@ -15,6 +15,13 @@ constexpr int THIN_FP_ANGLES = 8;   // angles per CTA (threadIdx.y)
 constexpr int THIN_BP_BATCH = 32;   // angles set up per block barrier
 constexpr int THIN_MAX = 4;         // "thin" = at most this many detector rows (FP) / z slices (BP)
 constexpr int THIN_BT = 4;          // batch items per thread in the batched instantiations
+#ifndef THIN_BP_UNROLL
+#define THIN_BP_UNROLL 4
+#endif
+constexpr int THIN_BP_ANGLES_IN_FLIGHT = THIN_BP_UNROLL;
+#ifndef THIN_BP_UNROLL
+#define THIN_BP_UNROLL 4
+#endif
 
 // All items of a batch share the geometry: a thread computes the tap offsets and weights of a
 // sample once and applies them to BT batch items (BT = 1 or THIN_BT), so the index arithmetic --
@@ -185,6 +192,8 @@ __global__ void __launch_bounds__(BP_THREADS) bp_thin_kernel(const BPArgs P, int
         }
         __syncthreads();
         if (!in_xy) continue;
+
+#pragma unroll THIN_BP_ANGLES_IN_FLIGHT  // angles in flight (independent loads of consecutive angles overlap)
         for (int j = 0; j < na; ++j) {
             const float *L = loc[j];
             float nu = fmaf(L[0], dx, fmaf(L[1], dy, fmaf(L[2], dz0, L[3])));

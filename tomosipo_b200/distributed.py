@@ -1,5 +1,5 @@
 """Multi-GPU projection: one process per GPU, angle-sharded projections,
-z-slab-sharded volumes (BASELINE.json north_star).
+z-sharded volumes (BASELINE.json north_star).
 
 The reference has no multi-GPU path for device arrays ("you must distribute the
 data over multiple GPUs yourself", ``doc/topics/operator.rst:246-249``); this is
@@ -20,17 +20,25 @@ FP is linear in the volume and independent per angle; BP is a sum over angles,
 so the sharded operator equals the single-GPU operator exactly up to the order
 of the fp32 sum over angle blocks.
 
-Overlap (``pipeline=True``, the default on NCCL).  The backprojection is cut
-into the ``N`` z-slabs of the sharding: slab ``j`` is back-projected by a
-sub-operator on ``vg[z_j]`` and handed to a second stream, which reduces it to
-its owner ``j`` while slab ``j + 1`` is being computed; only the last slab's
-reduce is exposed.  :func:`sirt` extends the same pipeline across the
-iteration boundary: the owner applies ``x_j -= C_j * slab`` as soon as its slab
-has arrived and broadcasts the new ``x_j`` into every rank's replicated volume,
-so the next forward projection needs no all-gather.  The residual
-``R * (A x - y)`` is formed in the forward projector's store
-(``tsp_project_fused``): an iteration is one FP launch group, ``N`` BP launches
-and ``2 N`` slab-sized collectives hidden behind them.
+Overlap (``chunks = K > 1``).  The z axis is cut into ``K`` chunks and every
+chunk into ``N`` pieces, one per rank: rank ``r`` owns piece ``r`` of *every*
+chunk, and its "slab" tensor is those ``K`` pieces stacked.  A chunk is then a
+contiguous z range on which the bandwidth-optimal collectives apply directly:
+the backprojection runs chunk by chunk (a sub-operator on ``vg[chunk]``) and
+chunk ``c`` is handed to a second stream for its ``reduce_scatter`` while chunk
+``c + 1`` is being computed, so only ``1/K`` of the exchange is exposed.
+:func:`sirt` extends the pipeline across the iteration boundary: as soon as a
+rank's piece of chunk ``c`` has arrived it applies ``x -= C * piece`` and the
+chunk is all-gathered into every rank's replicated volume, again behind the
+remaining chunks' kernels; the next forward projection starts without an
+all-gather.  The residual ``R * (A x - y)`` is formed in the forward
+projector's store (``tsp_project_fused``).  ``K = 1`` is the plain scheme of
+the table (contiguous slabs, one collective per call).
+
+(Measured on 8 x B200, profiles/r01_bench_n8_*.json: reducing each slab to its
+owner and broadcasting it back -- the first pipelining scheme tried -- loses to
+the un-overlapped collectives, because a reduce / broadcast of one slab uses
+one ring where all_gather / reduce_scatter use every NVLink port at once.)
 """
 import os
 
@@ -46,15 +54,29 @@ def shard_bounds(n, world, rank):
     return rank * n // world, (rank + 1) * n // world
 
 
+def default_chunks(nz, world):
+    """Chunks of the z axis for the overlapped exchange: 4 when the pieces stay >= 8 slices thick."""
+    if world == 1:
+        return 1
+    env = os.environ.get("TSP_SHARD_CHUNKS")  # measurement aid: 1 = one collective per call
+    if env:
+        return max(1, int(env))
+    for k in (4, 2):
+        if nz >= 8 * k * world:
+            return k
+    return 1
+
+
 class ShardedOperator:
-    """Angle-/slab-sharded view of ``ts.operator(vg, pg)`` over a process group.
+    """Angle-/z-sharded view of ``ts.operator(vg, pg)`` over a process group.
 
     ``make_local(vg, pg_block)`` builds the rank-local operator (default:
     ``ts.operator``); it only has to be callable as ``op(x, out=...)`` /
-    ``op.T(y, out=...)`` on the arrays it is given.
+    ``op.T(y, out=...)`` on the arrays it is given.  ``chunks``: see the module
+    docstring (default :func:`default_chunks`).
     """
 
-    def __init__(self, volume_geometry, projection_geometry, group=None, make_local=None, device=None, pipeline=None):
+    def __init__(self, volume_geometry, projection_geometry, group=None, make_local=None, device=None, chunks=None):
         if not isinstance(volume_geometry, ts.geometry.VolumeGeometry):
             raise TypeError("ShardedOperator needs an axis-aligned VolumeGeometry (z-slab sharding).")
         self.group = group
@@ -67,26 +89,78 @@ class ShardedOperator:
         if self.angle_hi <= self.angle_lo:
             raise ValueError(f"rank {self.rank} would own no projection angle ({pg.num_angles} angles, {self.world} ranks)")
         self.local_pg = pg[self.angle_lo:self.angle_hi]
-        self.local = (make_local or ts.operator)(volume_geometry, self.local_pg)
+        self._make_local = make_local or ts.operator
+        self.local = self._make_local(volume_geometry, self.local_pg)
         nz, ny, nx = volume_geometry.shape
-        self.slab_nz = -(-nz // self.world)  # slabs are padded to equal height for the collectives
-        self.z_lo = min(self.rank * self.slab_nz, nz)
-        self.z_hi = min(self.z_lo + self.slab_nz, nz)
+        self.chunks = default_chunks(nz, self.world) if chunks is None else (max(1, int(chunks)) if self.world > 1 else 1)
+        self.piece_nz = -(-nz // (self.chunks * self.world))  # pieces are padded to equal height for the collectives
+        self.chunk_nz = self.piece_nz * self.world
+        self.slab_nz = self.piece_nz * self.chunks
         self.vol_shape = (nz, ny, nx)
-        self.padded_shape = (self.slab_nz * self.world, ny, nx)
-        self.slab_shape = (self.slab_nz, ny, nx)          # rows >= z_hi - z_lo are padding (zeros)
+        self.padded_shape = (self.chunk_nz * self.chunks, ny, nx)
+        self.slab_shape = (self.slab_nz, ny, nx)          # rows beyond a piece's valid height are padding (zeros)
         self.proj_shape = (pg.det_shape[0], self.angle_hi - self.angle_lo, pg.det_shape[1])
+        # contiguous slab of the K = 1 scheme (None when the ownership is interleaved)
+        self.z_lo, self.z_hi = self.piece_bounds(0, self.rank) if self.chunks == 1 else (None, None)
         self.device = device
         self._full = None
         self._partial = None
-        self._transpose = _ShardedTranspose(self)
-        # z-slab sub-operators of the pipelined backprojection (built on first use)
-        self._make_local = make_local or ts.operator
-        if pipeline is None:  # TSP_SHARD_NO_PIPELINE: measurement aid (one reduce_scatter / all_gather per call)
-            pipeline = not os.environ.get("TSP_SHARD_NO_PIPELINE")
-        self.pipeline = bool(pipeline) and self.world > 1
-        self._slab_ops = None
+        self._chunk_ops = None
         self._comm_stream = None
+        self._transpose = _ShardedTranspose(self)
+        # The exchange only overlaps the kernels if its CTAs are scheduled ahead of the backprojector's
+        # queued ones: NCCL must run on high-priority streams.  With the default group that is a
+        # construction-time option the caller may not have set, so the overlapped scheme talks over its
+        # own communicator (measured at N = 8 without it: zero overlap, profiles/r01_sirt_breakdown_n8.txt).
+        if group is None and self.chunks > 1 and self._nccl():
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+            self.group = dist.new_group(backend="nccl", pg_options=opts)
+
+    # ------------------------------------------------------------- layout --
+    def piece_bounds(self, c, r):
+        """Unpadded z range ``[lo, hi)`` of rank ``r``'s piece of chunk ``c``."""
+        nz = self.vol_shape[0]
+        lo = min((c * self.world + r) * self.piece_nz, nz)
+        return lo, min(lo + self.piece_nz, nz)
+
+    def chunk_bounds(self, c):
+        """Unpadded z range ``[lo, hi)`` of chunk ``c``."""
+        nz = self.vol_shape[0]
+        lo = min(c * self.chunk_nz, nz)
+        return lo, min(lo + self.chunk_nz, nz)
+
+    def slab_pieces(self, rank=None):
+        """``[(slab_row, z_lo, z_hi)]``: rows ``slab_row : slab_row + z_hi - z_lo`` of the rank's slab
+        tensor hold the volume slices ``z_lo : z_hi``."""
+        r = self.rank if rank is None else rank
+        return [(c * self.piece_nz,) + self.piece_bounds(c, r) for c in range(self.chunks)]
+
+    def slab_geometry(self):
+        """Geometry of this rank's (unpadded) z-slab; only for the contiguous ``chunks == 1`` layout."""
+        if self.chunks != 1:
+            raise ValueError("the slab is not contiguous when chunks > 1; see slab_pieces()")
+        return self.volume_geometry[self.z_lo:self.z_hi]
+
+    def zero_padding_(self, slab):
+        """Zero the padding rows of a slab tensor (in place)."""
+        for row, lo, hi in self.slab_pieces():
+            slab[row + hi - lo: row + self.piece_nz].zero_()
+        return slab
+
+    def scatter_volume(self, full):
+        """This rank's padded slab of a replicated ``[nz, ny, nx]`` tensor."""
+        slab = torch.zeros(self.slab_shape, dtype=torch.float32, device=full.device)
+        for row, lo, hi in self.slab_pieces():
+            slab[row: row + hi - lo] = full[lo:hi]
+        return slab
+
+    def gather_volume(self, slab):
+        """Replicated ``[nz, ny, nx]`` tensor from all ranks' slabs."""
+        full = self._full_volume(slab)
+        slab = slab.contiguous()
+        for c in range(self.chunks):
+            self._all_gather_chunk(full, slab, c)
+        return full[: self.vol_shape[0]].clone()
 
     # ------------------------------------------------------------- buffers --
     def _full_volume(self, like):
@@ -95,93 +169,84 @@ class ShardedOperator:
         return self._full
 
     def _partial_volume(self, like):
-        """Second full-size buffer: the partial backprojection of this rank's angle block."""
+        """Second full-size buffer: the partial backprojection of this rank's angle block
+        (padding rows are never written and stay zero)."""
         if self._partial is None or self._partial.device != like.device:
             self._partial = torch.zeros(self.padded_shape, dtype=torch.float32, device=like.device)
         return self._partial
 
-    def slab_geometry(self):
-        """Geometry of this rank's (unpadded) z-slab."""
-        return self.volume_geometry[self.z_lo:self.z_hi]
-
-    def slab_bounds(self, j):
-        """Unpadded z range ``[lo, hi)`` of rank ``j``'s slab."""
-        nz = self.vol_shape[0]
-        lo = min(j * self.slab_nz, nz)
-        return lo, min(lo + self.slab_nz, nz)
-
-    def slab_operators(self):
-        """``[(z_lo, z_hi, operator on vg[z_lo:z_hi] x this rank's angle block)]``, empty slabs left out."""
-        if self._slab_ops is None:
+    def chunk_operators(self):
+        """``[(c, z_lo, z_hi, operator on vg[z_lo:z_hi] x this rank's angle block | None if empty)]``."""
+        if self._chunk_ops is None:
             ops = []
-            for j in range(self.world):
-                lo, hi = self.slab_bounds(j)
-                ops.append((j, lo, hi, self._make_local(self.volume_geometry[lo:hi], self.local_pg) if hi > lo else None))
-            self._slab_ops = ops
-        return self._slab_ops
+            for c in range(self.chunks):
+                lo, hi = self.chunk_bounds(c)
+                if self.chunks == 1:
+                    op = self.local
+                else:
+                    op = self._make_local(self.volume_geometry[lo:hi], self.local_pg) if hi > lo else None
+                ops.append((c, lo, hi, op))
+            self._chunk_ops = ops
+        return self._chunk_ops
 
-    def _side_stream(self, like):
+    def _streams(self, like):
         """(compute stream, communication stream) on CUDA, (None, None) on CPU."""
         if not like.is_cuda:
             return None, None
         if self._comm_stream is None or self._comm_stream.device != like.device:
-            self._comm_stream = torch.cuda.Stream(device=like.device)
+            self._comm_stream = torch.cuda.Stream(device=like.device, priority=-1)
         return torch.cuda.current_stream(like.device), self._comm_stream
-
-    def _bp_slabs(self, y_block, partial, after_slab):
-        """Back-project slab by slab into ``partial``; ``after_slab(j, slab_view)`` is issued on the
-        communication stream once slab ``j`` is complete (slab ``j + 1`` is computed meanwhile)."""
-        compute, comm = self._side_stream(y_block)
-        slabs = partial.view(self.world, *self.slab_shape)
-        if comm is not None:
-            comm.wait_stream(compute)                      # earlier users of `partial` / the replicated volume
-        for j, lo, hi, op in self.slab_operators():
-            if op is not None:
-                op.T(y_block, out=slabs[j][: hi - lo])
-            if comm is None:
-                after_slab(j, slabs[j])
-                continue
-            ev = torch.cuda.Event()
-            ev.record(compute)
-            comm.wait_event(ev)
-            with torch.cuda.stream(comm):
-                after_slab(j, slabs[j])
-        if comm is not None:
-            compute.wait_stream(comm)
-
-    def scatter_volume(self, full):
-        """This rank's padded slab of a replicated ``[nz, ny, nx]`` tensor."""
-        slab = torch.zeros(self.slab_shape, dtype=torch.float32, device=full.device)
-        slab[: self.z_hi - self.z_lo] = full[self.z_lo:self.z_hi]
-        return slab
-
-    def gather_volume(self, slab):
-        """Replicated ``[nz, ny, nx]`` tensor from all ranks' slabs."""
-        full = self._full_volume(slab)
-        self._all_gather(full, slab)
-        return full[: self.vol_shape[0]].clone()
 
     # --------------------------------------------------------- collectives --
     def _nccl(self):
         return dist.is_initialized() and dist.get_backend(self.group) == "nccl"
 
-    def _all_gather(self, full, slab):
-        if self.world == 1:
-            full.copy_(slab)
-        elif self._nccl():
-            dist.all_gather_into_tensor(full, slab.contiguous(), group=self.group)
-        else:  # gloo (CPU tests)
-            parts = list(full.view(self.world, *self.slab_shape).unbind(0))
-            dist.all_gather(parts, slab.contiguous(), group=self.group)
+    def _chunk_view(self, full, c):
+        return full[c * self.chunk_nz: (c + 1) * self.chunk_nz]
 
-    def _reduce_scatter(self, slab, full):
+    def _piece_view(self, slab, c):
+        return slab[c * self.piece_nz: (c + 1) * self.piece_nz]
+
+    def _all_gather_chunk(self, full, slab, c):
+        dst, src = self._chunk_view(full, c), self._piece_view(slab, c)
         if self.world == 1:
-            slab.copy_(full)
+            dst.copy_(src)
         elif self._nccl():
-            dist.reduce_scatter_tensor(slab, full, op=dist.ReduceOp.SUM, group=self.group)
-        else:  # gloo has no reduce_scatter: all_reduce, then keep the own slab
-            dist.all_reduce(full, op=dist.ReduceOp.SUM, group=self.group)
-            slab.copy_(full.view(self.world, *self.slab_shape)[self.rank])
+            dist.all_gather_into_tensor(dst, src, group=self.group)
+        else:  # gloo (CPU tests)
+            parts = list(dst.view(self.world, self.piece_nz, *self.slab_shape[1:]).unbind(0))
+            dist.all_gather(parts, src.contiguous(), group=self.group)
+
+    def _reduce_scatter_chunk(self, piece, full, c):
+        """``piece`` (one piece-sized tensor) = this rank's part of the sum over ranks of chunk ``c`` of ``full``."""
+        src = self._chunk_view(full, c)
+        if self.world == 1:
+            piece.copy_(src)
+        elif self._nccl():
+            dist.reduce_scatter_tensor(piece, src, op=dist.ReduceOp.SUM, group=self.group)
+        else:  # gloo has no reduce_scatter: all_reduce, then keep the own piece
+            dist.all_reduce(src, op=dist.ReduceOp.SUM, group=self.group)
+            piece.copy_(src.view(self.world, self.piece_nz, *self.slab_shape[1:])[self.rank])
+
+    def _bp_chunks(self, y_block, partial, after_chunk):
+        """Back-project chunk by chunk into ``partial``; ``after_chunk(c)`` is issued on the communication
+        stream once chunk ``c`` is complete (chunk ``c + 1`` is computed meanwhile)."""
+        compute, comm = self._streams(y_block)
+        if comm is not None:
+            comm.wait_stream(compute)                      # earlier users of the buffers the exchange touches
+        for c, lo, hi, op in self.chunk_operators():
+            if op is not None:
+                op.T(y_block, out=self._chunk_view(partial, c)[: hi - lo])
+            if comm is None:
+                after_chunk(c)
+                continue
+            ev = torch.cuda.Event()
+            ev.record(compute)
+            comm.wait_event(ev)
+            with torch.cuda.stream(comm):
+                after_chunk(c)
+        if comm is not None:
+            compute.wait_stream(comm)
 
     # ------------------------------------------------------------ operator --
     def __call__(self, x_slab, out=None):
@@ -191,35 +256,27 @@ class ShardedOperator:
         if self.world == 1:
             return self.local(x_slab, out=out)
         full = self._full_volume(x_slab)
-        self._all_gather(full, x_slab)
+        x_slab = x_slab.contiguous()
+        for c in range(self.chunks):
+            self._all_gather_chunk(full, x_slab, c)
         if out is None:
             out = torch.empty(self.proj_shape, dtype=torch.float32, device=x_slab.device)
         self.local(full[: self.vol_shape[0]], out=out)
         return out
 
     def _bp(self, y_block, out=None):
-        """``x_slab = reduce_scatter(A[angle block]^T y_block)``."""
+        """``x_slab = reduce_scatter(A[angle block]^T y_block)``, chunk by chunk."""
         if tuple(y_block.shape) != self.proj_shape:
             raise ValueError(f"Expected an angle block of shape {self.proj_shape}. Got {tuple(y_block.shape)}")
         if self.world == 1:
             return self.local.T(y_block, out=out)
         if out is None:
             out = torch.empty(self.slab_shape, dtype=torch.float32, device=y_block.device)
-        if self.pipeline:
-            partial = self._partial_volume(y_block)       # padding rows are never written: they stay zero
-            self._bp_slabs(y_block, partial, lambda j, slab: dist.reduce(slab, dst=self._global(j), group=self.group))
-            out.copy_(partial.view(self.world, *self.slab_shape)[self.rank])
-            return out
-        full = self._full_volume(y_block)
-        if self.padded_shape != self.vol_shape:
-            full[self.vol_shape[0]:].zero_()
-        self.local.T(y_block, out=full[: self.vol_shape[0]])
-        self._reduce_scatter(out, full)
+        elif not out.is_contiguous():
+            raise ValueError("out must be contiguous")
+        partial = self._partial_volume(y_block)
+        self._bp_chunks(y_block, partial, lambda c: self._reduce_scatter_chunk(self._piece_view(out, c), partial, c))
         return out
-
-    def _global(self, j):
-        """Global rank of group rank ``j`` (collectives with ``dst`` / ``src`` take global ranks)."""
-        return j if self.group is None else dist.get_global_rank(self.group, j)
 
     # ------------------------------------------------------ fused residual --
     def residual(self, x_full, y, R, out):
@@ -272,8 +329,8 @@ def sirt_weights(A, device, eps=None):
     C[C < eps] = float("inf")
     C.reciprocal_()
     x_tmp = torch.ones(A.slab_shape, device=device)
-    if A.z_hi - A.z_lo < A.slab_nz:
-        x_tmp[A.z_hi - A.z_lo:] = 0  # padding rows stay empty
+    if hasattr(A, "zero_padding_"):
+        A.zero_padding_(x_tmp)  # padding rows stay empty
     R = A(x_tmp)
     R[R < eps] = float("inf")
     R.reciprocal_()
@@ -291,10 +348,10 @@ def sirt(A, y, num_iterations, x=None, eps=None, weights=None):
     dev = y.device
     R, C = sirt_weights(A, dev, eps) if weights is None else weights
     y_tmp = torch.empty(A.proj_shape, device=dev)
-    x_tmp = torch.empty(A.slab_shape, device=dev)
     x_cur = torch.zeros(A.slab_shape, device=dev) if x is None else x
-    if getattr(A, "pipeline", False):
-        return _sirt_pipelined(A, y, R, C, x_cur, y_tmp, num_iterations)
+    if getattr(A, "world", 1) > 1:
+        return _sirt_overlapped(A, y, R, C, x_cur, y_tmp, num_iterations)
+    x_tmp = torch.empty(A.slab_shape, device=dev)
     for _ in range(num_iterations):
         A(x_cur, out=y_tmp)
         y_tmp -= y
@@ -305,24 +362,25 @@ def sirt(A, y, num_iterations, x=None, eps=None, weights=None):
     return x_cur
 
 
-def _sirt_pipelined(A, y, R, C, x_cur, y_tmp, num_iterations):
-    """The loop above with every exchange hidden behind the slab-wise backprojection
-    (module docstring, "Overlap").  Invariant at the top of an iteration: ``x_full`` holds
-    the current reconstruction on every rank, ``x_cur`` this rank's slab of it."""
+def _sirt_overlapped(A, y, R, C, x_cur, y_tmp, num_iterations):
+    """The loop above on a :class:`ShardedOperator` with the exchange behind the chunk-wise
+    backprojection (module docstring, "Overlap").  Invariant at the top of an iteration:
+    ``x_full`` holds the current reconstruction on every rank, ``x_cur`` this rank's pieces of it."""
+    if not x_cur.is_contiguous():
+        raise ValueError("x must be contiguous")
     x_full = A._full_volume(y)
-    A._all_gather(x_full, x_cur)
+    for c in range(A.chunks):
+        A._all_gather_chunk(x_full, x_cur, c)
     partial = A._partial_volume(y)
-    x_slabs = x_full.view(A.world, *A.slab_shape)
+    piece = torch.empty((A.piece_nz,) + tuple(A.slab_shape[1:]), dtype=torch.float32, device=y.device)
     y = y.contiguous()
 
-    def after_slab(j, slab):
-        dist.reduce(slab, dst=A._global(j), group=A.group)
-        if j == A.rank:
-            x_cur.addcmul_(C, slab, value=-1.0)           # x_j -= C_j * (sum over ranks of A_r^T y_tmp)
-            x_slabs[j].copy_(x_cur)
-        dist.broadcast(x_slabs[j], src=A._global(j), group=A.group)
+    def after_chunk(c):
+        A._reduce_scatter_chunk(piece, partial, c)
+        A._piece_view(x_cur, c).addcmul_(A._piece_view(C, c), piece, value=-1.0)   # x -= C * sum_r A_r^T y_tmp
+        A._all_gather_chunk(x_full, x_cur, c)
 
     for _ in range(num_iterations):
         A.residual(x_full[: A.vol_shape[0]], y, R, y_tmp)
-        A._bp_slabs(y_tmp, partial, after_slab)
+        A._bp_chunks(y_tmp, partial, after_chunk)
     return x_cur
