@@ -77,6 +77,30 @@ def cfg5():
     print(json.dumps({"config": "configs[4] learned-PD slab 1x256x256, 256 angles, 384 det, batch 16, fwd + bwd",
                       "ms_per_step": ms, "us_per_projector_application": ms * 1e3 / 64, "GUPS": upd / ms / 1e6}))
 
+# ---- the reference's own published SIRT benchmark (notebooks/sirt_benchmark.py:29-34, notebooks/README.md:43-47):
+#      200 iterations, ts.parallel 256^3 / 384 angles / 256 x 384 detector, torch CUDA tensors, in-place loop;
+#      published: 17.914 s on an RTX 2080 Ti (ASTRA's own SIRT3D_CUDA: 19.288 s)
+def published_sirt():
+    A = ts.operator(ts.volume(shape=256), ts.parallel(angles=384, shape=(256, 384)))
+    x = torch.from_numpy(ts.phantom.hollow_box(ts.data(A.domain)).data).cuda()
+    y = A(x)
+    from tomosipo_b200.algorithms import sirt, _weights
+    R, C = _weights(A, y, ts.epsilon)
+    def loop(n):                       # the reference's loop, line by line (sirt_benchmark.py:130-136)
+        x_cur = torch.zeros_like(x); y_tmp = torch.empty_like(y); x_tmp = torch.empty_like(x)
+        for _ in range(n):
+            A(x_cur, out=y_tmp); y_tmp -= y; y_tmp *= R
+            A.T(y_tmp, out=x_tmp); x_tmp *= C; x_cur -= x_tmp
+        return x_cur
+    loop(3); sync()
+    t0 = time.perf_counter(); xa = loop(200); sync(); dt = time.perf_counter() - t0
+    sirt(A, y, 3); sync()
+    t0 = time.perf_counter(); xb = sirt(A, y, 200); sync(); dtf = time.perf_counter() - t0
+    print(json.dumps({"config": "published analogue: SIRT 200 it, parallel 256^3, 384 angles, 256x384 (sirt_benchmark.py)",
+                      "reference_loop_s": dt, "fused_s": dtf, "published_s_2080ti": 17.914,
+                      "GUPS_reference_loop": 2 * 256 ** 3 * 384 * 200 / dt / 1e9,
+                      "rel_diff_loop_vs_fused": float((xa - xb).norm() / xa.norm())}))
+
 with warnings.catch_warnings():
     warnings.simplefilter("ignore")
-    cfg1(); cfg2(); cfg5()
+    cfg1(); cfg2(); cfg5(); published_sirt()

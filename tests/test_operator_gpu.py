@@ -299,3 +299,32 @@ def test_full_size_properties():
     assert abs(float(ones[n // 2 - 1, 180, 383]) - 1.0) < 1e-3
     out = torch.zeros_like(ones)
     assert torch.equal(A(torch.ones(A.domain_shape, device="cuda"), out=out), ones)  # deterministic
+
+
+def test_full_size_properties_1024():
+    """BASELINE configs[3] (cone 1024^3, 1440 angles, 1024 x 1536) on one GPU: size-independent properties."""
+    n = 1024
+    free, _ = torch.cuda.mem_get_info()
+    if free < 60 * 2 ** 30:
+        pytest.skip("needs ~50 GB of device memory")
+    vg = ts.volume(shape=n, size=1)
+    pg = ts.cone(angles=1440, shape=(n, 1536), size=(1.875, 2.8125), src_orig_dist=4, src_det_dist=6)
+    A = ts.operator(vg, pg)
+    assert A.astra_projector.info().n_march_x + A.astra_projector.info().n_march_y == 1440
+    ones = A(torch.ones(A.domain_shape, device="cuda"))
+    assert abs(float(ones[n // 2, 0, 768]) - 1.0) < 1e-3       # central chord of the unit cube
+    assert abs(float(ones[n // 2 - 1, 360, 767]) - 1.0) < 1e-3
+    assert float(ones.min()) >= 0.0 and float(ones.max()) < 1.8  # longest chord of a unit cube is sqrt(3)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    x = torch.rand(A.domain_shape, device="cuda", generator=g)
+    y = A(x)
+    y -= ones
+    assert float(y.max()) <= 1e-4                              # monotone: 0 <= x <= 1  =>  A x <= A 1
+    y += ones
+    lhs = (y * ones).sum(dtype=torch.float64)
+    bp = A.T(ones)
+    rhs = (x * bp).sum(dtype=torch.float64)
+    assert abs(float(lhs / rhs) - 1) < 0.01                    # scaled adjoint
+    del y, x
+    out = torch.zeros_like(bp)
+    assert torch.equal(A.T(ones, out=out), bp)                 # deterministic
