@@ -190,7 +190,12 @@ static void plan_fp_tma_group(const tsp_projector *pr, FPGroup &grp)
     grp.box_w = grp.box_h = 0;
     // rows per thread: 8 amortises the per-slice synchronisation over twice the samples; small
     // detectors keep 4 so that the grid still fills the GPU.  TSP_FP_R overrides (tuning aid).
-    grp.rows_per_thread = (g.det_rows >= 128 && (long long)g.det_rows * g.det_cols >= 256LL * 256) ? 8 : 4;
+    // (the row blocks of the host pipeline are 32-128 rows of a wide detector: judged by the CTA count, not by the rows)
+    {
+        const long long ctas8 = (long long)((g.det_cols + FPT_TU - 1) / FPT_TU) * ((g.det_rows + 31) / 32) *
+                                (long long)((grp.angles.size() + 1) / 2);
+        grp.rows_per_thread = (g.det_rows >= 32 && ctas8 >= 8LL * 148) ? 8 : 4;
+    }
     if (const char *e = getenv("TSP_FP_R")) grp.rows_per_thread = atoi(e) == 8 ? 8 : 4;
     const int tile_v = 4 * grp.rows_per_thread;
     int box_w = 0, box_h = 0;
@@ -986,17 +991,40 @@ static bool plan_host_pipeline(tsp_projector *pr)
     const int cz = chunk_size(g.nz), cv = chunk_size(g.det_rows);
     std::vector<tsp_projector::HostChunk> bp, fp;
     bool ok = true;
-    for (int z0 = 0; z0 < g.nz && ok; z0 += cz) {
+    // uniform chunks, except where a transfer cannot hide behind a kernel: the slab the BP starts with (its
+    // rows must arrive before any kernel runs) and the row block the FP ends with (its download follows the
+    // last kernel) are halved
+    std::vector<std::pair<int, int>> zr, vr;
+    for (int z0 = 0; z0 < g.nz; z0 += cz) zr.push_back({z0, std::min(g.nz, z0 + cz)});
+    for (int v0 = 0; v0 < g.det_rows; v0 += cv) vr.push_back({v0, std::min(g.det_rows, v0 + cv)});
+    if (!getenv("TSP_HOST_UNIFORM")) {
+        size_t mid = 0;
+        for (size_t i = 0; i < zr.size(); ++i)
+            if (zr[i].first <= (g.nz - 1) / 2 && (g.nz - 1) / 2 < zr[i].second) mid = i;
+        if (zr.size() > 1 && zr[mid].second - zr[mid].first >= 64) {
+            const int h = (zr[mid].first + zr[mid].second) / 2;
+            const std::pair<int, int> hi{h, zr[mid].second};
+            zr[mid].second = h;
+            zr.insert(zr.begin() + mid + 1, hi);
+        }
+        if (vr.size() > 1 && vr.back().second - vr.back().first >= 64) {
+            const int h = (vr.back().first + vr.back().second) / 2;
+            const std::pair<int, int> hi{h, vr.back().second};
+            vr.back().second = h;
+            vr.push_back(hi);
+        }
+    }
+    for (size_t i = 0; i < zr.size() && ok; ++i) {
         tsp_projector::HostChunk c;
-        c.z0 = z0; c.z1 = std::min(g.nz, z0 + cz);
+        c.z0 = zr[i].first; c.z1 = zr[i].second;
         slab_row_range(pr, c.z0, c.z1, c.v0, c.v1);
         c.sub = make_sub_projector(pr, c.z0, c.z1, c.v0, c.v1);
         ok = c.sub != nullptr;
         bp.push_back(c);
     }
-    for (int v0 = 0; v0 < g.det_rows && ok; v0 += cv) {
+    for (size_t i = 0; i < vr.size() && ok; ++i) {
         tsp_projector::HostChunk c;
-        c.v0 = v0; c.v1 = std::min(g.det_rows, v0 + cv);
+        c.v0 = vr[i].first; c.v1 = vr[i].second;
         block_z_range(pr, c.v0, c.v1, c.z0, c.z1);
         c.sub = make_sub_projector(pr, c.z0, c.z1, c.v0, c.v1);
         ok = c.sub != nullptr;
@@ -1006,6 +1034,20 @@ static bool plan_host_pipeline(tsp_projector *pr)
         for (auto &c : bp) tsp_projector_destroy(c.sub);
         for (auto &c : fp) tsp_projector_destroy(c.sub);
         return false;
+    }
+    // BP: start with the slab whose shadow is the smallest (fewest rows to upload before the first kernel can
+    // run: for a cone beam the central one) and work outwards, so that each later slab only adds a few rows
+    if (!getenv("TSP_HOST_BP_INORDER") && !bp.empty()) {
+        size_t first = 0;
+        for (size_t i = 1; i < bp.size(); ++i)
+            if (bp[i].v1 - bp[i].v0 < bp[first].v1 - bp[first].v0) first = i;
+        std::vector<tsp_projector::HostChunk> ord;
+        ord.push_back(bp[first]);
+        for (size_t d = 1; d < bp.size(); ++d) {
+            if (first + d < bp.size()) ord.push_back(bp[first + d]);
+            if (first >= d) ord.push_back(bp[first - d]);
+        }
+        bp.swap(ord);
     }
     if (getenv("TSP_DEBUG")) {
         for (auto &c : bp) fprintf(stderr, "[tsp] host BP chunk: z [%d, %d) <- rows [%d, %d)\n", c.z0, c.z1, c.v0, c.v1);
