@@ -138,3 +138,28 @@ def test_single_process_sharded_operator_is_identity_wrapper():
     torch.testing.assert_close(S(x), OracleOperator(vg, pg)(x))
     with pytest.raises(TypeError):
         ShardedOperator(vg.to_vec(), pg)
+
+
+def test_default_chunks_and_piece_layout(monkeypatch):
+    from tomosipo_b200.distributed import default_chunks
+
+    monkeypatch.delenv("TSP_SHARD_CHUNKS", raising=False)
+    assert default_chunks(512, 1) == 1 and default_chunks(512, 8) == 4 and default_chunks(1024, 8) == 4
+    assert default_chunks(128, 8) == 2 and default_chunks(50, 4) == 1
+    monkeypatch.setenv("TSP_SHARD_CHUNKS", "1")
+    assert default_chunks(512, 8) == 1
+    # every slice is owned exactly once, whatever the padding
+    for nz, world, k in ((512, 8, 4), (50, 4, 3), (9, 2, 2), (7, 8, 1), (100, 3, 4)):
+        S = ShardedOperator.__new__(ShardedOperator)
+        S.world, S.chunks, S.vol_shape = world, k, (nz, 4, 4)
+        S.piece_nz = -(-nz // (k * world))
+        S.chunk_nz = S.piece_nz * world
+        owned = np.zeros(nz, int)
+        for r in range(world):
+            for row, lo, hi in S.slab_pieces(rank=r):
+                assert row % S.piece_nz == 0 and 0 <= hi - lo <= S.piece_nz
+                owned[lo:hi] += 1
+        assert (owned == 1).all()
+        for c in range(k):
+            lo, hi = S.chunk_bounds(c)
+            assert lo == min(c * S.chunk_nz, nz) and hi == min((c + 1) * S.chunk_nz, nz)
