@@ -226,8 +226,15 @@ def run_ours(args):
         bp()
     torch.cuda.synchronize()
 
+    def launches_so_far():
+        """Kernels launched by this rank's projectors: the local operator and, at N > 1, the z-chunk sub-operators."""
+        ops = {id(S.local): S.local}
+        if world > 1:
+            ops.update({id(op): op for _, _, _, op in S.chunk_operators() if op is not None})
+        return sum(op.astra_projector.info().kernel_launches for op in ops.values())
+
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
-    launches0 = P.info().kernel_launches
+    launches0 = launches_so_far()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
@@ -251,7 +258,7 @@ def run_ours(args):
         t = torch.tensor([total_ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms = float(t.item())
-    launches = P.info().kernel_launches - launches0
+    launches = launches_so_far() - launches0
     fp_ms = float(np.mean([e[0].elapsed_time(e[1]) for e in ev]))
     bp_ms = float(np.mean([e[1].elapsed_time(e[2]) for e in ev]))
 
