@@ -14,6 +14,10 @@
  *   - TSP_MEM_DEVICE calls are asynchronous on the given CUDA stream;
  *     TSP_MEM_HOST calls return after the result is back in host memory
  *     (ASTRA's synchronous contract, tomosipo/astra.py:146-153).
+ *   - a projector is immutable after creation: TSP_MEM_DEVICE calls may be issued
+ *     concurrently from several host threads / streams (per-call scratch comes
+ *     from the stream-ordered pool, TMA descriptors travel by value), and they
+ *     capture into CUDA graphs.
  *   - there is no CPU fallback: without a usable CUDA device every compute
  *     entry point fails with TSP_ERR_CUDA.
  */

@@ -249,8 +249,39 @@ def test_stream_semantics():
     assert torch.equal(y, ref)
 
 
-# ----------------------------------------------- properties at the benchmark size
-@pytest.mark.slow
+def test_concurrent_host_threads_share_a_projector():
+    """One projector, two host threads, two streams: device calls are independent (per-call scratch from the
+    stream-ordered pool, descriptors by value, immutable geometry tables)."""
+    import threading
+
+    A = ts.operator(ts.volume(shape=(64, 64, 64), size=1),
+                    ts.cone(angles=48, shape=(64, 96), size=(1.875, 2.8125), src_orig_dist=4, src_det_dist=6))
+    g = torch.Generator(device="cuda").manual_seed(0)
+    xs = [torch.rand(A.domain_shape, device="cuda", generator=g) for _ in range(2)]
+    refs = [(A(x), A.T(A(x))) for x in xs]
+    torch.cuda.synchronize()
+    out, errors = [None, None], []
+
+    def work(i):
+        try:
+            s = torch.cuda.Stream()
+            with torch.cuda.stream(s):
+                for _ in range(20):
+                    y = A(xs[i])
+                    xb = A.T(y)
+            s.synchronize()
+            out[i] = (y, xb)
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    threads = [threading.Thread(target=work, args=(i,)) for i in range(2)]
+    [t.start() for t in threads]
+    [t.join() for t in threads]
+    assert not errors
+    for i in range(2):
+        assert torch.equal(out[i][0], refs[i][0]) and torch.equal(out[i][1], refs[i][1])
+
+
 def test_device_calls_capture_into_a_cuda_graph():
     """FP + BP on device tensors are plain stream work (kernel launches with by-value TMA descriptors,
     stream-ordered scratch): they capture into a CUDA graph and replay on new data."""
@@ -278,6 +309,8 @@ def test_device_calls_capture_into_a_cuda_graph():
         assert torch.equal(y, y_ref) and torch.equal(xb, A.T(y_ref))
 
 
+# ----------------------------------------------- properties at the benchmark size
+@pytest.mark.slow
 def test_full_size_properties():
     n = 512
     vg = ts.volume(shape=n, size=1)

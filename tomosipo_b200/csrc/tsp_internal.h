@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
@@ -78,10 +79,11 @@ struct tsp_projector {
     std::vector<tsp::BPAngle> bp_angles;
     std::map<int, tsp::DeviceState> dev;
     std::mutex mu;
-    int64_t launches = 0;
-    int bp_uses_tma = 0;
-    int fp_uses_transpose = 0;
-    int fp_uses_tma = 0;
+    // introspection counters: written by concurrent callers, hence atomic
+    std::atomic<int64_t> launches{0};
+    std::atomic<int> bp_uses_tma{0};
+    std::atomic<int> fp_uses_transpose{0};
+    std::atomic<int> fp_uses_tma{0};
     // Host-array pipeline: the problem cut into sub-problems (BP: z-slabs of the volume with the
     // detector rows their cone shadow covers; FP: detector row blocks), each with its own
     // sub-projector, so that H2D / D2H of one chunk overlaps the kernels of another.
@@ -91,5 +93,5 @@ struct tsp_projector {
     };
     std::vector<HostChunk> host_bp, host_fp;
     bool host_planned = false;
-    int host_pipelined = 0;  // last host-array call ran the chunked pipeline
+    std::atomic<int> host_pipelined{0};  // last host-array call ran the chunked pipeline
 };

@@ -1102,7 +1102,7 @@ static int project_host_pipelined(tsp_projector *pr, DeviceState *st, int device
             const int64_t l0 = c.sub->launches;
             rc = launch_fp(c.sub, sst, dvol + (size_t)c.z0 * slice, dproj + (size_t)c.v0 * row, 0, stream);
             pr->launches += c.sub->launches - l0;
-            pr->fp_uses_tma = c.sub->fp_uses_tma; pr->fp_uses_transpose = c.sub->fp_uses_transpose;
+            pr->fp_uses_tma = c.sub->fp_uses_tma.load(); pr->fp_uses_transpose = c.sub->fp_uses_transpose.load();
             if (rc) break;
             CUDA_TRY(cudaEventRecord(ev_done[k], stream));
             CUDA_TRY(cudaStreamWaitEvent(st->s_out, ev_done[k], 0));
@@ -1129,7 +1129,7 @@ static int project_host_pipelined(tsp_projector *pr, DeviceState *st, int device
             const int64_t l0 = c.sub->launches;
             rc = launch_bp(c.sub, sst, dvol + (size_t)c.z0 * slice, dproj + (size_t)c.v0 * row, 0, stream);
             pr->launches += c.sub->launches - l0;
-            pr->bp_uses_tma = c.sub->bp_uses_tma;
+            pr->bp_uses_tma = c.sub->bp_uses_tma.load();
             if (rc) break;
             CUDA_TRY(cudaEventRecord(ev_done[k], stream));
             CUDA_TRY(cudaStreamWaitEvent(st->s_out, ev_done[k], 0));
