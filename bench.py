@@ -355,8 +355,10 @@ def run_ours(args):
         "fp_gups": upd / (fp_ms * 1e-3) / 1e9, "bp_gups": upd / (bp_ms * 1e-3) / 1e9,
         "fp_updates_per_clk_per_sm": upd / (fp_ms * 1e-3) / (sm_mhz * 1e6) / 148,
         "bp_updates_per_clk_per_sm": upd / (bp_ms * 1e-3) / (sm_mhz * 1e6) / 148,
-        "ceiling_updates_per_clk_per_sm": 8.0,
-        "ceiling_note": "shared-memory gather: 128 B/clk/SM / (4 taps x 4 B) (measured LDS crossbar rate, B300_MICROARCH.md)",
+        "ceiling_updates_per_clk_per_sm": 8.9,
+        "ceiling_note": "measured on B200 (scratch/ubench/gather_ceiling.cu, profiles/r01_gather_ceiling.txt): 4 conflict-free "
+                        "LDS.32 taps per update and nothing else = 8.91 updates/clk/SM; with scalar bilinear arithmetic 6.33; "
+                        "the 3-row BP loop (6 taps per voxel pair) 9.52",
         "fp_kernel": fp_name, "bp_kernel": bp_name,
     }
     t_dom = traffic.get(dom) if world == 1 and not big else None  # the ncu capture is of cfg 3 on one GPU

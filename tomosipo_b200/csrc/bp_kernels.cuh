@@ -487,7 +487,10 @@ constexpr int BP_TMA_PITCH = 68;
 constexpr int BP_TMA_PITCH_B = 60;  // alternative: consecutive rows start 4 banks *earlier*
 constexpr int BP_TMA_CONSUMERS = BP_TX * BP_TY;
 constexpr int BP_TMA_THREADS = BP_TMA_CONSUMERS + 32;
-__host__ __device__ constexpr int bp_tma_stages(int zpt) { return zpt >= 32 ? 4 : (zpt >= 16 ? 6 : 8); }
+#ifndef BP_TMA_STAGES_Z32
+#define BP_TMA_STAGES_Z32 4  // ring depth at 32 voxels per thread (tuning: -DBP_TMA_STAGES_Z32=n)
+#endif
+__host__ __device__ constexpr int bp_tma_stages(int zpt) { return zpt >= 32 ? BP_TMA_STAGES_Z32 : (zpt >= 16 ? 6 : 8); }
 __host__ __device__ constexpr size_t bp_tma_box_bytes(int zpt) { return (size_t)bp_wv(zpt) * BP_TMA_PITCH * 4; }
 // ring stages are 128-byte aligned (TMA destination alignment)
 __host__ __device__ constexpr size_t bp_tma_stage_bytes(int zpt) { return (bp_tma_box_bytes(zpt) + 127) / 128 * 128; }
