@@ -111,6 +111,14 @@ typedef struct tsp_projector_info {
 } tsp_projector_info;
 int tsp_projector_get_info(const tsp_projector *projector, tsp_projector_info *info);
 
+/* Plan of the host-array pipeline (TSP_MEM_HOST calls on large problems are cut into sub-problems
+ * whose transfers overlap the kernels: what ASTRA's CompositeGeometryManager does for ndarray inputs,
+ * reference doc/topics/operator.rst:226-261).  Chunk k of `direction` works on volume slices
+ * [z0, z1) and detector rows [v0, v1): out[4k .. 4k+3] = z0, z1, v0, v1, in execution order.
+ * Returns the number of chunks (0: this geometry is not pipelined), writes at most max_chunks of
+ * them.  Host-only (no CUDA call); used by the tests to check the bounds against the geometry. */
+int tsp_projector_host_plan(tsp_projector *projector, int direction, int32_t *out, int max_chunks);
+
 /* Per-angle FP marching axis (0 = x, 1 = y, 2 = z), for parity checks. */
 int tsp_projector_marching_axes(const tsp_projector *projector, int32_t *axes);
 

@@ -72,6 +72,7 @@ EXPORTED_SYMBOLS = (
     "tsp_last_error",
     "tsp_sirt",
     "tsp_project_fused",
+    "tsp_projector_host_plan",
 )
 
 
@@ -123,6 +124,8 @@ def lib():
         L.tsp_sirt.restype = ctypes.c_int
         L.tsp_project_fused.argtypes = [vp, ctypes.c_int, vp, vp, vp, vp, ctypes.c_int, vp]
         L.tsp_project_fused.restype = ctypes.c_int
+        L.tsp_projector_host_plan.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.c_int]
+        L.tsp_projector_host_plan.restype = ctypes.c_int
         _lib = L
         return _lib
 
@@ -202,6 +205,15 @@ class Projector:
         vp = ctypes.c_void_p
         _check(lib().tsp_project_fused(self._handle, int(direction), vp(vol_ptr), vp(proj_ptr), vp(sub_ptr), vp(mul_ptr),
                                        int(device), vp(stream)))
+
+    def host_plan(self, direction):
+        """``[(z0, z1, v0, v1)]`` of the host-array pipeline for FP / BP, in execution order ([] = not pipelined)."""
+        n = lib().tsp_projector_host_plan(self._handle, int(direction), None, 0)
+        if n < 0:
+            _check(n)
+        buf = (ctypes.c_int32 * (4 * max(n, 1)))()
+        n = lib().tsp_projector_host_plan(self._handle, int(direction), buf, n)
+        return [tuple(buf[4 * k: 4 * k + 4]) for k in range(n)]
 
     def info(self):
         info = tsp_projector_info()

@@ -1058,6 +1058,19 @@ static bool plan_host_pipeline(tsp_projector *pr)
     return true;
 }
 
+extern "C" int tsp_projector_host_plan(tsp_projector *pr, int direction, int32_t *out, int max_chunks)
+{
+    if (!pr || (!out && max_chunks > 0)) return fail(TSP_ERR_INVALID, "NULL argument");
+    if (direction != TSP_FP && direction != TSP_BP) return fail(TSP_ERR_INVALID, "direction must be TSP_FP or TSP_BP");
+    if (!plan_host_pipeline(pr)) return 0;
+    const std::vector<tsp_projector::HostChunk> &chunks = direction == TSP_FP ? pr->host_fp : pr->host_bp;
+    for (size_t k = 0; k < chunks.size() && (int)k < max_chunks; ++k) {
+        out[4 * k + 0] = chunks[k].z0; out[4 * k + 1] = chunks[k].z1;
+        out[4 * k + 2] = chunks[k].v0; out[4 * k + 3] = chunks[k].v1;
+    }
+    return (int)chunks.size();
+}
+
 // One FP (SET) or BP (SET) between host arrays, chunked and pipelined over three streams.
 static int project_host_pipelined(tsp_projector *pr, DeviceState *st, int device, int direction, float *vol, float *proj,
                                   cudaStream_t stream)
