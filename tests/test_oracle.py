@@ -119,3 +119,32 @@ def test_supersampling_converges_to_finer_grid():
     yf = fine.fp(x)
     avg = yf.reshape(8, 2, 5, 10, 2).mean(axis=(1, 4))
     np.testing.assert_allclose(coarse.fp(x), avg, atol=1e-12)
+
+
+def test_bp_of_ones_closed_forms():
+    """Backprojection of a stack of ones (the C = 1 / A.T(1) of README.md:151-154) in closed form.
+
+    Bilinear interpolation of a constant is exact, so a voxel whose shadow stays on the detector gets
+    n_angles x (ray-density weight) x (voxel volume):
+      parallel:  1 / (pixel area)                       -> n_angles * s^3 / (pu * pv)
+      cone, voxel on the rotation axis: (SDD / SOD)^2 / (pixel area) at every angle
+                                                        -> n_angles * s^3 * (SDD / SOD)^2 / (pu * pv)
+    """
+    n, na = 32, 20
+    lo, hi = unit_cube(n)
+    s = 1.0 / n
+    t = np.linspace(0, 2 * np.pi, na, endpoint=False)
+    pu, pv = 1.5 / 48, 1.25 / 32
+    P = O.OracleProjector(O.PARALLEL_VEC, (n, n, n), lo, hi, (32, 48), O.parallel_vectors(t, pu, pv))
+    x = P.bp(np.ones(P.proj_shape))
+    inner = x[8:24, 8:24, 8:24]
+    assert np.allclose(inner, na * s ** 3 / (pu * pv), rtol=1e-12)
+    sod, odd = 4.0, 2.0
+    pu, pv = 2.8125 / 48, 1.875 / 32
+    Pc = O.OracleProjector(O.CONE_VEC, (n + 1, n + 1, n + 1), [-(n + 1) * s / 2] * 3, [(n + 1) * s / 2] * 3, (32, 48),
+                           O.cone_vectors(t, pu, pv, sod, odd))
+    xc = Pc.bp(np.ones(Pc.proj_shape))
+    c = n // 2                                        # odd grid: voxel c is centred on the rotation axis, z = 0
+    assert abs(xc[c, c, c] / (na * s ** 3 * ((sod + odd) / sod) ** 2 / (pu * pv)) - 1) < 1e-12
+    # off the mid-plane the weight uses the distance along the central ray only: same value along the axis
+    assert abs(xc[c + 5, c, c] / xc[c, c, c] - 1) < 1e-12
