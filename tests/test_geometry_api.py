@@ -160,3 +160,26 @@ def test_random_geometries_fuzz_conversion():
         np.testing.assert_allclose(v[:, 9:12][:, ::-1], pg.det_v)
         centre = pg.lower_left_corner + pg.det_shape[0] / 2 * pg.det_v + pg.det_shape[1] / 2 * pg.det_u
         np.testing.assert_allclose(centre, pg.det_pos, atol=1e-9)
+
+
+def test_fdk_angle_table_of_a_circular_scan():
+    """Host part of algorithms.fdk: per-angle constants recovered from the cone-beam vectors
+    (pixel pitches, SDD, SOD, principal point) for a circular scan and for a shifted detector."""
+    import tomosipo_b200 as ts
+    from tomosipo_b200.algorithms import _fdk_angle_table
+
+    vg = ts.volume(shape=(8, 10, 12), size=(0.8, 1.0, 1.2))
+    pg = ts.cone(angles=7, shape=(16, 24), size=(3.2, 3.6), src_orig_dist=5, src_det_dist=8)
+    t = _fdk_angle_table(ts.operator(vg, pg))
+    assert np.allclose(t["pu"], 3.6 / 24) and np.allclose(t["pv"], 3.2 / 16)
+    assert np.allclose(t["sdd"], 8) and np.allclose(t["sod"], 5)
+    assert np.allclose(t["ppu"], 0, atol=1e-12) and np.allclose(t["ppv"], 0, atol=1e-12)
+    assert np.isclose(t["vox"], 0.1 ** 3)
+    # detector shifted by 2.5 pixels along u and -1 pixel along v: the principal point moves the other way
+    v = pg.to_vec()
+    shifted = ts.cone_vec(shape=v.det_shape, src_pos=v.src_pos, det_pos=v.det_pos + 2.5 * v.det_u - 1.0 * v.det_v,
+                          det_v=v.det_v, det_u=v.det_u)
+    t2 = _fdk_angle_table(ts.operator(vg, shifted))
+    assert np.allclose(t2["ppu"], -2.5) and np.allclose(t2["ppv"], 1.0) and np.allclose(t2["sdd"], 8)
+    with pytest.raises(TypeError):
+        _fdk_angle_table(ts.operator(vg, ts.parallel(angles=5, shape=(16, 24))))
