@@ -128,3 +128,93 @@ def test_vector_volume_is_unrotated():
     assert A.astra_compat_vg == ts.volume(shape=(4, 5, 6), pos=0, size=(2, 2.5, 3))
     assert A.astra_compat_pg == (T * R).inv * pg.to_vec()
     assert A.domain_shape == (4, 5, 6) and A.range_shape == (8, 7, 9)
+
+
+def test_cupy_link_against_a_stand_in_module(monkeypatch):
+    """CuPy is absent from the image: exercise CupyLink's own logic (reference links/cupy.py:25-159: coercion
+    warnings, shape checks, pointer export, same-device allocation) against a numpy-backed stand-in for the
+    handful of cupy names it touches."""
+    import contextlib
+    import importlib
+    import sys
+    import types
+
+    class _Dev:
+        def __init__(self, id_=0):
+            self.id = id_
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *a):
+            return False
+
+        def __eq__(self, other):
+            return isinstance(other, _Dev) and other.id == self.id
+
+    class FakeArray:
+        """The slice of cupy.ndarray the link uses, over a numpy array (not a subclass: numpy's link must not take it)."""
+        device = _Dev(0)
+
+        def __init__(self, a):
+            self.a = a
+
+        shape = property(lambda self: self.a.shape)
+        dtype = property(lambda self: self.a.dtype)
+        flags = property(lambda self: {"C_CONTIGUOUS": self.a.flags["C_CONTIGUOUS"]})
+        data = property(lambda self: types.SimpleNamespace(ptr=self.a.ctypes.data))  # cupy: MemoryPointer
+
+        def astype(self, dt):
+            return FakeArray(self.a.astype(dt))
+
+        def copy(self):
+            return FakeArray(self.a.copy())
+
+        def __setitem__(self, k, v):
+            self.a[k] = v.a if isinstance(v, FakeArray) else v
+
+    def wrap(a):
+        return FakeArray(np.asarray(a))
+
+    fake = types.ModuleType("cupy")
+    fake.ndarray = FakeArray
+    fake.float32 = np.float32
+    fake.zeros = lambda shape, dtype=np.float32: wrap(np.zeros(shape, dtype))
+    fake.empty = lambda shape, dtype=np.float32: wrap(np.empty(shape, dtype))
+    fake.full = lambda shape, value, dtype=np.float32: wrap(np.full(shape, value, dtype))
+    fake.ascontiguousarray = lambda a: wrap(np.ascontiguousarray(a.a))
+    fake.cuda = types.SimpleNamespace(get_current_stream=lambda: types.SimpleNamespace(ptr=1234))
+    monkeypatch.setitem(sys.modules, "cupy", fake)
+    sys.modules.pop("tomosipo_b200.links.cupy", None)
+    n_backends = len(ts.links.base.backends)
+    try:
+        mod = importlib.import_module("tomosipo_b200.links.cupy")
+        CupyLink = mod.CupyLink
+        vg = ts.volume(shape=(2, 3, 4))
+        a = wrap(np.arange(24, dtype=np.float32).reshape(2, 3, 4))
+        lk = ts.link(vg, a)
+        assert isinstance(lk, CupyLink) and lk.data is a
+        rb = lk.linked_data
+        assert (rb.ptr, rb.shape, rb.kind, rb.device, rb.stream) == (a.a.ctypes.data, (2, 3, 4), "device", 0, 1234)
+        with pytest.raises(ValueError):
+            CupyLink((2, 3, 5), a)
+        with pytest.raises(ValueError):
+            CupyLink((2, 3, 4), np.zeros((2, 3, 4), np.float32))          # a plain ndarray is not a cupy array
+        with pytest.warns(UserWarning, match="float32"):
+            assert CupyLink((2, 3, 4), wrap(np.zeros((2, 3, 4)))).data.dtype == np.float32
+        with pytest.warns(UserWarning, match="contiguous"):
+            t = CupyLink((2, 3, 4), wrap(np.zeros((4, 3, 2), np.float32).T))
+        assert t.data.flags["C_CONTIGUOUS"]
+        s0 = CupyLink((2, 3, 4), wrap(np.float32(3.0)))                       # scalars fill a new array
+        assert s0.data.shape == (2, 3, 4) and float(s0.data.a.min()) == 3.0
+        z, f, e, c = lk.new_zeros((1, 2, 3)), lk.new_full((1, 2, 3), 2.5), lk.new_empty((3, 2, 1)), lk.clone()
+        assert z.data.shape == (1, 2, 3) and float(z.data.a.sum()) == 0 and float(f.data.a.mean()) == 2.5
+        assert e.data.shape == (3, 2, 1) and c.data is not a and np.array_equal(c.data.a, a.a)
+        with pytest.raises(AttributeError):
+            lk.data = a
+        assert lk.__compatible_with__(c) is True and lk.__compatible_with__(ts.link(vg, np.zeros((2, 3, 4), np.float32))) is NotImplemented
+        with lk.context():
+            pass
+    finally:
+        del ts.links.base.backends[n_backends:]
+        sys.modules.pop("tomosipo_b200.links.cupy", None)
