@@ -37,6 +37,8 @@ sys.path.insert(0, ROOT)
 
 METRIC = "FP3D+BP3D GUPS (voxels x angles / s), cone_vec 512^3 x 720 angles"
 UNIT = "GUPS"
+WORKLOAD_CFG3 = "cone_vec 512^3 vol, 720 angles, 512x768 det (BASELINE configs[2]), FP+BP per step"
+WORKLOAD_CFG4 = "cone_vec 1024^3 vol, 1440 angles, 1024x1536 det (BASELINE configs[3]), FP+BP per step"
 
 
 def workload(n=512, n_angles=720):
@@ -49,9 +51,14 @@ def workload(n=512, n_angles=720):
     return vg, pg
 
 
+TRAFFIC_FILE = "profiles/r02_traffic.json"
+TRAFFIC_SOURCE = (f"{TRAFFIC_FILE}: dram__bytes_read.sum + dram__bytes_write.sum per launch from the builder's committed "
+                  "`ncu --set full` capture of this workload (not measured in this run)")
+
+
 def load_traffic():
     """DRAM bytes per launch of the two hot kernels, from the committed `ncu --set full` capture."""
-    p = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    p = os.path.join(ROOT, TRAFFIC_FILE)
     if os.path.exists(p):
         with open(p) as f:
             return json.load(f)
@@ -129,52 +136,140 @@ def omp_threads():
     return int(v) if v and v.isdigit() else (os.cpu_count() or 1)
 
 
-def cpu_sample(n=192, n_angles=96, repeats=1):
-    """Bounded CPU sample of the same workload: (n^3, n_angles, n x 1.5n)."""
+CPU_SAMPLE_ANGLES = 16
+
+
+def cpu_sample(n=512, n_total_angles=720, n_sample=CPU_SAMPLE_ANGLES, repeats=1):
+    """Bounded CPU sample of the SAME workload: the headline volume and detector (n^3, n x 1.5n) and every
+    (n_total / n_sample)-th of its angles.  FP and BP cost are linear in the number of angles (each angle is an
+    independent pass over the volume), so GUPS on the sample is GUPS on the whole angle set; the sampled angles
+    cover the circle, hence the same mix of x- and y-marching rays."""
     from oracle import oracle as O
 
     det = (n, 3 * n // 2)
-    vec = O.cone_vectors(np.linspace(0, 2 * np.pi, n_angles, endpoint=False), 2.8125 / det[1], 1.875 / det[0], 4.0, 2.0)
+    every = max(1, n_total_angles // n_sample)
+    t = np.linspace(0, 2 * np.pi, n_total_angles, endpoint=False)[::every][:n_sample]
+    vec = O.cone_vectors(t, 2.8125 / det[1], 1.875 / det[0], 4.0, 2.0)
     Q = O.OracleProjector(O.CONE_VEC, (n, n, n), [-0.5] * 3, [0.5] * 3, det, vec)
     x = O.hollow_box(n)
     y = np.zeros(Q.proj_shape, np.float32)
     xb = np.zeros(Q.vol_shape, np.float32)
-    Q.fp(x, out=y, dtype=np.float32)  # warm caches / thread pool
     t0 = time.perf_counter()
     for _ in range(repeats):
         Q.fp(x, out=y, dtype=np.float32)
         Q.bp(y, out=xb, dtype=np.float32)
     dt = (time.perf_counter() - t0) / repeats
-    updates = 2.0 * n ** 3 * n_angles
-    return updates / dt / 1e9, dt, f"cone {n}^3 x {n_angles} angles x {n}x{3 * n // 2} det, FP+BP, fp32 OpenMP port"
+    updates = 2.0 * n ** 3 * len(t)
+    return updates / dt / 1e9, dt, (f"cone_vec {n}^3 vol, {n}x{3 * n // 2} det, {len(t)} of the {n_total_angles} angles "
+                                    f"(every {every}th), FP+BP, fp32 OpenMP port of the same arithmetic")
 
 
 def run_reference(args):
-    """--impl reference: the CPU port on all host cores (rank 0 only)."""
+    """--impl reference: the CPU port on all host cores (rank 0 only), same volume / detector / metric."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     # all host threads, also under torchrun (which exports OMP_NUM_THREADS=1); set before the OpenMP runtime starts
     os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)
     cores = omp_threads()
-    for _ in range(args.warmup):
-        cpu_sample(96, 48)
+    # One short pass warms the thread pool / page cache and measures the rate; the per-step sample is then sized so
+    # that exactly --steps steps end within ~3 minutes on this host: 4 ... 16 of the 720 angles, a multiple of 4.
+    _, dt4, _ = cpu_sample(n_sample=4)
+    per_angle = dt4 / 4
+    n_sample = int(180.0 / max(args.steps, 1) / per_angle) // 4 * 4
+    n_sample = max(4, min(CPU_SAMPLE_ANGLES, n_sample))
     vals, ms = [], []
-    for _ in range(args.steps):
-        g, dt, sample = cpu_sample()
+    for i in range(args.steps):
+        g, dt, sample = cpu_sample(n_sample=n_sample)
         vals.append(g); ms.append(dt * 1e3)
     v = float(np.mean(vals))
     line = {
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": float(np.mean(ms)), "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "cone_vec 512^3 vol, 720 angles, 512x768 det, FP+BP per step (bounded CPU sample)",
+        "config": {"workload": WORKLOAD_CFG3, "phantom": "hollow_box",
+                   "sample": f"each step = FP+BP over {n_sample} of the 720 angles, spread over the circle (cost is linear in "
+                             "angles); GUPS counts the sampled updates only",
                    "note": "ASTRA (the reference engine) is CUDA-only and absent; CPU port of the same arithmetic"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line))
+
+
+def sharded_parity_check(ts, ShardedOperator, dev, world):
+    """The angle- / z-sharded operator (NCCL all_gather / reduce_scatter, chunked overlap) against the single-GPU
+    operator on a 128^3 x 96-angle cone problem: relative L2 of this rank's FP angle block and BP z-slab, max over
+    ranks.  Differences come only from the order of the fp32 sum over angle blocks (~1e-7)."""
+    import torch
+    import torch.distributed as dist
+
+    n, na = 128, 96
+    vg = ts.volume(shape=n, size=1)
+    pg = ts.cone(angles=na, shape=(n, 3 * n // 2), size=(1.875, 2.8125), src_orig_dist=4, src_det_dist=6).to_vec()
+    S = ShardedOperator(vg, pg)
+    A = ts.operator(vg, pg)
+    g = torch.Generator(device=dev).manual_seed(7)           # same seed on every rank: replicated inputs
+    x_full = torch.rand(tuple(A.domain_shape), device=dev, generator=g)
+    w_full = torch.rand(tuple(A.range_shape), device=dev, generator=g)
+    y_ref = A(x_full)[:, S.angle_lo:S.angle_hi, :]
+    y_blk = S(S.scatter_volume(x_full))
+    e_fp = torch.linalg.vector_norm(y_blk - y_ref) / torch.linalg.vector_norm(y_ref)
+    xb_ref = S.scatter_volume(A.T(w_full))
+    xb_slab = S.T(w_full[:, S.angle_lo:S.angle_hi, :].contiguous())
+    S.zero_padding_(xb_slab)
+    e_bp = torch.linalg.vector_norm(xb_slab - xb_ref) / torch.linalg.vector_norm(xb_ref)
+    t = torch.stack([e_fp, e_bp]).float()
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return {"fp": float(t[0]), "bp": float(t[1]), "problem": f"cone {n}^3 x {na} angles x {n}x{3 * n // 2}, {S.chunks} z-chunks",
+            "ranks": world}
+
+
+def cfg4_sirt(ts, ShardedOperator, dev, world, local, iterations=3):
+    """SIRT ms / iteration at BASELINE configs[3] (1024^3, 1440 angles, 1024 x 1536) on `world` GPUs: fused tsp_sirt at
+    N = 1, the sharded overlapped loop at N > 1; one warm-up iteration, weights are set-up (untimed)."""
+    import torch
+    import torch.distributed as dist
+
+    vg, pg = workload(1024, 1440)
+    S = ShardedOperator(vg, pg)
+    y = torch.empty(S.proj_shape, device=dev, dtype=torch.float32)
+    g = torch.Generator(device=dev).manual_seed(11)
+    y.uniform_(0.0, 1.0, generator=g)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if world == 1:
+        from tomosipo_b200.algorithms import _weights
+
+        A = S.local
+        R_, C_ = _weights(A, y, ts.epsilon)
+        xs = torch.zeros(tuple(A.domain_shape), device=dev)
+        y_tmp = torch.empty_like(y)
+        strm = torch.cuda.current_stream().cuda_stream
+        run = lambda k: A.astra_projector.sirt(xs.data_ptr(), y.data_ptr(), R_.data_ptr(), C_.data_ptr(), y_tmp.data_ptr(), k,
+                                               device=local, stream=strm)
+    else:
+        from tomosipo_b200.distributed import sirt as sirt_sharded, sirt_weights
+
+        W_ = sirt_weights(S, dev)
+        xs = torch.zeros(S.slab_shape, device=dev)
+        run = lambda k: sirt_sharded(S, y, k, x=xs, weights=W_)
+    run(1)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0.record()
+    run(iterations)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iterations
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"workload": "cone 1024^3 vol, 1440 angles, 1024x1536 det (BASELINE configs[3]), SIRT", "ms_per_iter": ms,
+            "iters_per_s": 1e3 / ms, "iterations": iterations, "n_gpus": world,
+            "gups": 2.0 * 1024.0 ** 3 * 1440 / (ms * 1e-3) / 1e9}
 
 
 def run_ours(args):
@@ -270,7 +365,7 @@ def run_ours(args):
     e2e = None
     if not args.skip_e2e:
         try:
-            e2e_steps = max(1, min(args.steps, 3))
+            e2e_steps = max(10, min(args.steps, 20))
             if world == 1:
                 # one GPU: numpy arrays straight into A(x) / A.T(y) (the library's chunked copy / compute pipeline)
                 xh = torch.from_numpy(ts.phantom.hollow_box(ts.data(vg)).data).pin_memory().numpy()
@@ -285,24 +380,41 @@ def run_ours(args):
                 h2d = 4 * (nvox + npix)   # FP: volume in; BP: projections in
                 d2h = 4 * (npix + nvox)   # FP: projections out; BP: volume out
             else:
-                # N GPUs: every rank keeps its shard of both arrays in pinned host memory: the z-slab goes up, the sharded
-                # operator all-gathers and projects, the angle block comes down; then the block goes up, is back-projected
-                # and reduce-scattered, and the slab comes down.  The whole job moves each array once per direction.
+                # N GPUs: every rank keeps its shard of each array in pinned host memory.  Per step and rank: slab up ->
+                # all_gather + FP -> angle block down, and (independent data, as for a user holding measured projections)
+                # block up -> BP + reduce_scatter -> slab down.  The uploads run on a copy-in stream, the FP result's
+                # download on a copy-out stream behind the BP kernels; the step ends when both results are on the host.
+                # The whole job moves each array once per direction.
                 xs_h = torch.empty(S.slab_shape, dtype=torch.float32).pin_memory()
                 xs_h.copy_(x)
+                w_h = torch.empty(S.proj_shape, dtype=torch.float32).pin_memory()
+                w_h.copy_(y)
                 yb_h = torch.empty(S.proj_shape, dtype=torch.float32).pin_memory()
                 xb_h = torch.empty(S.slab_shape, dtype=torch.float32).pin_memory()
-                xd = torch.empty_like(x)
+                xd, wd = torch.empty_like(x), torch.empty_like(y)
+                s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+                ev_x, ev_w, ev_fp = torch.cuda.Event(), torch.cuda.Event(), torch.cuda.Event()
 
                 def e2e_step():
-                    xd.copy_(xs_h, non_blocking=True)        # H2D: this rank's slab
+                    cur = torch.cuda.current_stream()
+                    s_in.wait_stream(cur)
+                    with torch.cuda.stream(s_in):
+                        xd.copy_(xs_h, non_blocking=True)    # H2D: this rank's slab
+                        ev_x.record()
+                        wd.copy_(w_h, non_blocking=True)     # H2D: this rank's angle block (behind the FP kernels)
+                        ev_w.record()
+                    cur.wait_event(ev_x)
                     S(xd, out=y)                             # all_gather + FP of the rank's angle block
-                    yb_h.copy_(y, non_blocking=True)         # D2H: angle block
-                    y.copy_(yb_h, non_blocking=True)         # H2D: angle block (stream-ordered behind the D2H)
-                    S.T(y, out=xb)                           # BP + reduce_scatter
+                    ev_fp.record(cur)
+                    s_out.wait_event(ev_fp)
+                    with torch.cuda.stream(s_out):
+                        yb_h.copy_(y, non_blocking=True)     # D2H: FP result (behind the BP kernels)
+                    cur.wait_event(ev_w)
+                    S.T(wd, out=xb)                          # BP + reduce_scatter
                     xb_h.copy_(xb, non_blocking=True)        # D2H: slab
-                    torch.cuda.synchronize()
-                    return float(xb_h[0, 0, 0])
+                    cur.wait_stream(s_out)
+                    torch.cuda.synchronize()                 # both results are on the host: end of the step
+                    return float(xb_h[0, 0, 0]) + float(yb_h[0, 0, 0])
 
                 h2d = 4 * (int(np.prod(S.slab_shape)) + int(np.prod(S.proj_shape))) * world
                 d2h = h2d
@@ -323,7 +435,8 @@ def run_ours(args):
             e2e = {"value": updates_step * e2e_steps / e2e_s / 1e9, "unit": UNIT,
                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                    "path": "A(x) / A.T(y) on pinned numpy arrays (library host pipeline)" if world == 1 else
-                           "pinned host shards <-> ShardedOperator (slab up, angle block down; block up, slab down)"}
+                           "pinned host shards <-> ShardedOperator (slab up -> FP -> block down | block up -> BP -> slab down; "
+                           "copies on side streams, one synchronize per step)"}
         except Exception as exc:  # keep the device-resident line even if the host leg cannot run (e.g. no pinned memory)
             print(f"[bench] host-array leg failed on rank {rank}: {exc!r}", file=sys.stderr)
             e2e = None
@@ -365,6 +478,34 @@ def run_ours(args):
         sirt_ms = float(t.item()) / sirt_iters
         del xs, W_
 
+    # kernel names from the projectors that actually ran: FP on the rank-local operator, BP on it too at N = 1 but on the
+    # z-chunk sub-operators at N > 1 (ShardedOperator._bp_chunks)
+    info = P.info()
+    bp_infos = [info] if world == 1 else [op.astra_projector.info() for _, _, _, op in S.chunk_operators() if op is not None]
+    bp_name = "bp_tma_kernel" if all(i.bp_uses_tma for i in bp_infos) else "bp_kernel"
+    fp_name = "fp_tma_kernel" if info.fp_uses_tma else "fp_cols_kernel"
+    n_chunks = S.chunks
+
+    # ---- N > 1: the sharded operator against the single-GPU operator on a small problem (every rank, max over ranks)
+    sharded_parity = None
+    if world > 1:
+        try:
+            sharded_parity = sharded_parity_check(ts, ShardedOperator, dev, world)
+        except Exception as exc:
+            print(f"[bench] sharded parity check failed on rank {rank}: {exc!r}", file=sys.stderr)
+
+    # ---- BASELINE configs[3] (cone 1024^3 x 1440 angles x 1024x1536): SIRT ms / iteration, the configuration the
+    # north_star's scaling target is written on; carried in every line so that the 1 -> 8 GPU curve is driver-visible
+    cfg4 = None
+    if not big and not args.skip_cfg4:
+        del x, y, xb
+        S = A = P = None
+        torch.cuda.empty_cache()
+        try:
+            cfg4 = cfg4_sirt(ts, ShardedOperator, dev, world, local, iterations=3)
+        except Exception as exc:
+            print(f"[bench] cfg4 SIRT leg failed on rank {rank}: {exc!r}", file=sys.stderr)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -373,9 +514,6 @@ def run_ours(args):
     peaks, peak_kind = load_peaks()
     traffic = load_traffic()
     b_alg = 4.0 * (nvox + npix)  # bytes per FP or per BP launch (SET mode), SURVEY.md 8d
-    info = P.info()
-    bp_name = "bp_tma_kernel" if info.bp_uses_tma else "bp_kernel"
-    fp_name = "fp_tma_kernel" if info.fp_uses_tma else "fp_cols_kernel"
     dom = bp_name if bp_ms >= fp_ms else fp_name
     dom_ms = max(bp_ms, fp_ms)
     achieved = b_alg / (dom_ms * 1e-3) / 1e9
@@ -400,22 +538,24 @@ def run_ours(args):
         "metric": METRIC.replace("512^3 x 720", "1024^3 x 1440") if big else METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": ("cone_vec 1024^3 vol, 1440 angles, 1024x1536 det (BASELINE configs[3]), FP+BP per step" if big else
-                                "cone_vec 512^3 vol, 720 angles, 512x768 det (BASELINE configs[2]), FP+BP per step"),
+        "config": {"workload": WORKLOAD_CFG4 if big else WORKLOAD_CFG3,
                    "phantom": "hollow_box", "l2": ("inputs (4.3 GB + 9.1 GB) larger than L2" if big else
                                                    "inputs (537 MB + 1132 MB) larger than L2"),
                    "parallelism": "single GPU" if world == 1 else
-                   f"angle-sharded x{world}, z-sharded volume: NCCL all_gather -> FP; BP in {S.chunks} z-chunks -> NCCL reduce_scatter per chunk (overlapped)"},
+                   f"angle-sharded x{world}, z-sharded volume: NCCL all_gather -> FP; BP in {n_chunks} z-chunks -> NCCL reduce_scatter per chunk (overlapped)"},
         "fp_ms": fp_ms, "bp_ms": bp_ms,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                     "frac": achieved / peaks["hbm_gbs"], "traffic": t_dom, "peak_kind": peak_kind,
+                     "frac": achieved / peaks["hbm_gbs"], "traffic": t_dom,
+                     "traffic_source": (TRAFFIC_SOURCE if t_dom is not None else None), "peak_kind": peak_kind,
                      "algorithmic_bytes_per_launch": b_alg, "interp": interp},
         "cpu_baseline": cpu_base,
         "e2e": e2e,
         "sirt": {"iters_per_s": 1e3 / sirt_ms, "ms_per_iter": sirt_ms, "iterations": sirt_iters,
                  "path": "tsp_sirt (fused epilogues)" if world == 1 else
-                 f"sharded: fused residual FP; BP in {S.chunks} z-chunks, each chunk's NCCL reduce_scatter + update + "
+                 f"sharded: fused residual FP; BP in {n_chunks} z-chunks, each chunk's NCCL reduce_scatter + update + "
                  "all_gather on a side stream behind the next chunk's kernel"},
+        "cfg4_sirt": cfg4,
+        "sharded_parity_rel_l2": sharded_parity,
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
@@ -433,6 +573,7 @@ def main():
     ap.add_argument("--workload", default="cfg3", choices=["cfg3", "cfg4"],
                     help="cfg3 = BASELINE configs[2] (the headline, default); cfg4 = configs[3], 1024^3 x 1440 (scaling study)")
     ap.add_argument("--skip-e2e", action="store_true", help="leave out the host-array leg (scaling study at cfg4)")
+    ap.add_argument("--skip-cfg4", action="store_true", help="leave out the 1024^3 x 1440 SIRT sub-record")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -98,7 +98,23 @@ void tsp_projector_destroy(tsp_projector *projector);
 int tsp_project(tsp_projector *projector, int direction, int additive, void *vol, void *proj,
                 int batch, int memory_kind, int device, void *cuda_stream);
 
-/* Introspection used by the tests and by bench.py. */
+/*
+ * Host arrays over several GPUs: what `astra.set_gpu_index([0, 1, ...])` switches on for ndarray inputs in the
+ * reference (doc/topics/operator.rst:226-245, "the ASTRA-toolbox will automatically divide all projection and
+ * backprojection over all four GPUs").  vol / proj are HOST arrays (pinned memory overlaps best); the chunks of the
+ * host-array plan are dealt out to `devices` and each device runs the copy / compute pipeline over its share from
+ * its own host thread.  Returns when the result is in host memory.  Additive calls and problems too small to be
+ * chunked run on devices[0].
+ *
+ * Device memory of every TSP_MEM_HOST call is bounded: when the two arrays would not fit the budget
+ * (TSP_HOST_MEM_CAP_MB, default: the device's free memory minus a reserve) the pipeline works out of a ring of three
+ * chunk-sized buffer pairs instead of whole arrays (out-of-core, as ASTRA's CompositeGeometryManager splits jobs).
+ */
+int tsp_project_multi(tsp_projector *projector, int direction, int additive, void *vol, void *proj,
+                      const int *devices, int n_devices);
+
+/* Introspection used by the tests and by bench.py.  The *_uses_* / host_* fields describe the LAST call on the
+ * projector; with concurrent callers they are informational only. */
 typedef struct tsp_projector_info {
     int32_t n_angles;
     int32_t n_march_x, n_march_y, n_march_z; /* FP marching-axis census */
@@ -108,6 +124,8 @@ typedef struct tsp_projector_info {
     int32_t fp_uses_transpose;                /* last FP built an (x<->y) transposed volume */
     int32_t fp_uses_tma;                      /* last FP used the TMA-staged kernel for >= 1 angle group */
     int32_t host_pipelined;                   /* last TSP_MEM_HOST call ran the chunked copy/compute pipeline */
+    int32_t host_ring;                        /* ... out of a bounded ring of chunk buffers (out-of-core mode) */
+    int32_t host_devices;                     /* ... on this many devices (tsp_project_multi) */
 } tsp_projector_info;
 int tsp_projector_get_info(const tsp_projector *projector, tsp_projector_info *info);
 
@@ -118,6 +136,15 @@ int tsp_projector_get_info(const tsp_projector *projector, tsp_projector_info *i
  * Returns the number of chunks (0: this geometry is not pipelined), writes at most max_chunks of
  * them.  Host-only (no CUDA call); used by the tests to check the bounds against the geometry. */
 int tsp_projector_host_plan(tsp_projector *projector, int direction, int32_t *out, int max_chunks);
+
+/* The backprojector's voxel -> detector map of one angle, evaluated on the host from the very table
+ * the kernels read: for a point xyz of the world frame (the frame of win_min / win_max and of the
+ * vectors; x, y, z order) out = {U, V, w}, detector pixel (iv, iu) spanning [iu, iu+1) x [iv, iv+1)
+ * and w the ray-density weight (voxel volume not included).  This is what the reference exposes as
+ * {Cone,Parallel}VectorGeometry.project_point (tomosipo/geometry/cone_vec.py:306-326,
+ * parallel_vec.py:313-330; known answers tests/geometry/test_cone_vec.py:143-173), which the parity
+ * tests hold it against.  Host-only (no CUDA call). */
+int tsp_projector_bp_map(const tsp_projector *projector, int angle, const double *xyz, double *out);
 
 /* Per-angle FP marching axis (0 = x, 1 = y, 2 = z), for parity checks. */
 int tsp_projector_marching_axes(const tsp_projector *projector, int32_t *axes);

@@ -66,6 +66,12 @@ def lib():
             bp.argtypes = [gp, p, p, ctypes.c_int]
             bp.restype = ctypes.c_int
         _lib.oracle_marching_axes_f64.argtypes = [gp, ctypes.POINTER(ctypes.c_int32)]
+        i32p, f32p, f64p = (ctypes.POINTER(t) for t in (ctypes.c_int32, ctypes.c_float, ctypes.c_double))
+        _lib.oracle_fp_angles_mixed.argtypes = [gp, f32p, i32p, ctypes.c_int, i32p, ctypes.c_int, f64p]
+        _lib.oracle_bp_window_mixed.argtypes = [gp, f32p, i32p, i32p, f64p]
+        _lib.oracle_bp_map.argtypes = [gp, ctypes.c_int, f64p, f64p]
+        for sfx in ("f64", "f32"):
+            getattr(_lib, f"oracle_set_weight_bits_{sfx}").argtypes = [ctypes.c_int]
     return _lib
 
 
@@ -123,10 +129,65 @@ class OracleProjector:
         self._run("bp", dtype, out, proj, additive)
         return out
 
+    # ---- spot checks at benchmark sizes: float32 storage (what the GPU saw), fp64 arithmetic
+    def fp_angles(self, vol_f32, angle_list, row_list=None):
+        """``(A vol)[row_list, angle_list, :]`` (all rows by default) in fp64 from a float32 volume."""
+        vol = np.ascontiguousarray(vol_f32, dtype=np.float32)
+        assert vol.shape == self.vol_shape
+        idx = np.ascontiguousarray(angle_list, dtype=np.int32)
+        rows = np.ascontiguousarray(np.arange(self.g.det_rows) if row_list is None else row_list, dtype=np.int32)
+        assert idx.min() >= 0 and idx.max() < self.g.n_angles and rows.min() >= 0 and rows.max() < self.g.det_rows
+        out = np.zeros((len(rows), len(idx), self.g.det_cols))
+        i32p = ctypes.POINTER(ctypes.c_int32)
+        rc = lib().oracle_fp_angles_mixed(ctypes.byref(self.g), vol.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                          idx.ctypes.data_as(i32p), len(idx), rows.ctypes.data_as(i32p), len(rows),
+                                          out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        assert rc == 0
+        return out
+
+    def bp_window(self, proj_f32, z, y, x):
+        """``(A^T proj)[z0:z1, y0:y1, x0:x1]`` in fp64 from a float32 projection stack; z, y, x are (lo, hi)."""
+        proj = np.ascontiguousarray(proj_f32, dtype=np.float32)
+        assert proj.shape == self.proj_shape
+        lo = np.array([x[0], y[0], z[0]], dtype=np.int32)
+        hi = np.array([x[1], y[1], z[1]], dtype=np.int32)
+        assert (lo >= 0).all() and (hi > lo).all() and (hi <= np.array(self.vol_shape[::-1])).all()
+        out = np.zeros((z[1] - z[0], y[1] - y[0], x[1] - x[0]))
+        i32p = ctypes.POINTER(ctypes.c_int32)
+        rc = lib().oracle_bp_window_mixed(ctypes.byref(self.g), proj.ctypes.data_as(ctypes.POINTER(ctypes.c_float)),
+                                          lo.ctypes.data_as(i32p), hi.ctypes.data_as(i32p),
+                                          out.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        assert rc == 0
+        return out
+
+    def bp_map(self, angle, xyz):
+        """(U, V, weight) of a world-frame point (x, y, z) on the detector of ``angle``: the backprojector's map."""
+        p = np.ascontiguousarray(xyz, dtype=np.float64)
+        out = np.zeros(3)
+        f64p = ctypes.POINTER(ctypes.c_double)
+        lib().oracle_bp_map(ctypes.byref(self.g), int(angle), p.ctypes.data_as(f64p), out.ctypes.data_as(f64p))
+        return out
+
     def marching_axes(self):
         axes = np.zeros(self.g.n_angles, dtype=np.int32)
         lib().oracle_marching_axes_f64(ctypes.byref(self.g), axes.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)))
         return axes
+
+
+class astra_texture_weights:
+    """Context manager: interpolation weights rounded to ``bits`` fractional bits (8 = CUDA's texture unit,
+    which is what ASTRA interpolates with); see ``oracle_set_weight_bits`` in tsp_oracle.c."""
+
+    def __init__(self, bits=8):
+        self.bits = bits
+
+    def __enter__(self):
+        for sfx in ("f64", "f32"):
+            getattr(lib(), f"oracle_set_weight_bits_{sfx}")(self.bits)
+
+    def __exit__(self, *exc):
+        for sfx in ("f64", "f32"):
+            getattr(lib(), f"oracle_set_weight_bits_{sfx}")(0)
 
 
 # --------------------------------------------------------------------------

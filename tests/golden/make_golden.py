@@ -136,6 +136,33 @@ def describe(ts, vg, pg):
             "kind": np.array([0 if apg["type"] == "cone_vec" else 1]), "project_point": pp}
 
 
+def project_point_cases(ts):
+    """Geometries with orthogonal detector axes (the reference's project_point divides by |u|^2 and |v|^2
+    separately, which is the detector coordinate only then): name -> projection geometry."""
+    rng = np.random.default_rng(4321)
+    R = (ts.rotate(pos=(0.1, -0.2, 0.3), axis=(1.0, 0.5, -0.2), angles=0.7) * ts.translate((0.3, -0.4, 0.5)))
+    angles = rng.uniform(0, 2 * np.pi, size=9)
+    return {
+        # tests/geometry/test_cone_vec.py:143-173 of the reference (its own known answers live on these two)
+        "ref_test_coarse": ts.cone(angles=1, shape=(10, 40), size=(30, 80), src_orig_dist=10, src_det_dist=10).to_vec(),
+        "ref_test_fine": ts.cone(angles=1, shape=(100, 400), size=(30, 80), src_orig_dist=10, src_det_dist=10).to_vec(),
+        "cfg3_cone": ts.cone(angles=24, shape=(32, 48), size=(1.875, 2.8125), src_orig_dist=4, src_det_dist=6).to_vec(),
+        "cone_vec_R": R * ts.cone(angles=angles, shape=(6, 7), size=(3, 4), src_orig_dist=5, src_det_dist=8).to_vec(),
+        "parallel": ts.parallel(angles=angles, shape=(9, 11), size=(2.0, 3.5)).to_vec(),
+        "par_vec_R": R * ts.parallel(angles=angles, shape=(6, 7), size=(3, 4)).to_vec(),
+    }
+
+
+def describe_project_point(ts, pg, seed):
+    rng = np.random.default_rng(seed)
+    pts = rng.uniform(-0.6, 0.6, size=(16, 3))               # (z, y, x), the reference's point order
+    pp = np.stack([pg.project_point(p) for p in pts])        # (16, n_angles, 2) = (v, u) in pixels from the detector centre
+    apg = pg.to_astra()
+    return {"points_zyx": pts, "project_point": pp, "vectors": np.asarray(apg["Vectors"], dtype=np.float64),
+            "det": np.array([apg["DetectorRowCount"], apg["DetectorColCount"]]),
+            "kind": np.array([0 if apg["type"] == "cone_vec" else 1])}
+
+
 def main():
     install_stubs()
     sys.path.insert(0, REF)
@@ -153,6 +180,13 @@ def main():
     out["transform/perspective"] = ts.from_perspective(pos=(1, 2, 3), w=(0, 1, 0), v=(0, 0, 2), u=(3, 0, 0)).matrix
     np.savez_compressed(os.path.join(HERE, "geometry_golden.npz"), **out)
     print(f"wrote {len(out)} arrays")
+    # voxel -> detector map (the (U, V) level of the backprojector) from the reference's project_point
+    out = {}
+    for i, (name, pg) in enumerate(project_point_cases(ts).items()):
+        for k, v in describe_project_point(ts, pg, 100 + i).items():
+            out[f"{name}/{k}"] = v
+    np.savez_compressed(os.path.join(HERE, "project_point_golden.npz"), **out)
+    print(f"wrote {len(out)} project_point arrays")
 
 
 if __name__ == "__main__":

@@ -314,3 +314,77 @@ def test_host_array_pipeline_matches_single_shot(kindname):
     assert rel_l2(outs[0][1], outs[1][1].astype(np.float64)) <= 2e-6
     assert rel_l2(outs[0][0], Q.fp(x.astype(np.float64))) <= TOL
     assert rel_l2(outs[0][1], Q.bp(outs[0][0].astype(np.float64))) <= TOL
+
+
+@pytest.mark.parametrize("kindname", ["cone", "parallel"])
+def test_host_array_pipeline_out_of_core_ring(kindname):
+    """Bounded device memory (ASTRA's CompositeGeometryManager splits jobs that do not fit,
+    reference doc/topics/operator.rst:226-261): with a device-memory budget below the size of the two arrays the
+    host-array pipeline runs out of a ring of three chunk-sized buffer pairs; same numbers as the whole-array mode
+    and the fp64 oracle.  A budget too small for the ring itself is a MemoryError, not a crash."""
+    from tomosipo_b200 import _backend as B
+
+    n, det = 256, (256, 384)
+    if kindname == "cone":
+        kind = O.CONE_VEC
+        vec = O.cone_vectors(np.linspace(0, 2 * np.pi, 60, endpoint=False), 2.8125 / det[1], 1.875 / det[0], 4.0, 2.0)
+    else:
+        kind = O.PARALLEL_VEC
+        vec = O.parallel_vectors(np.linspace(0, np.pi, 60, endpoint=False), 1.6 / det[1], 1.2 / det[0])
+    win = [(-.5, .5)] * 3
+    x = np.random.default_rng(6).random((n, n, n)).astype(np.float32)
+    total_mb = (x.size + det[0] * 60 * det[1]) * 4 / 2 ** 20          # 64 + 22.5 MB
+    outs = []
+    for cap in (None, 64):                                             # MB; None: whole-array mode
+        kw = {"TSP_HOST_PIPELINE_MIN_MB": 0, "TSP_HOST_CHUNKS": 8}
+        if cap:
+            kw["TSP_HOST_MEM_CAP_MB"] = cap
+            assert cap < total_mb
+        with env(**kw):
+            P, Q = make(kind, (n, n, n), win, det, vec)
+            y = np.zeros(Q.proj_shape, np.float32)
+            P.project(B.FP, False, x.ctypes.data, y.ctypes.data, B.MEM_HOST, 0, 0)
+            assert P.info().host_pipelined == 1 and P.info().host_ring == (1 if cap else 0)
+            xb = np.zeros((n, n, n), np.float32)
+            P.project(B.BP, False, xb.ctypes.data, y.ctypes.data, B.MEM_HOST, 0, 0)
+            assert P.info().host_pipelined == 1 and P.info().host_ring == (1 if cap else 0)
+        outs.append((y, xb))
+    assert rel_l2(outs[1][0], outs[0][0].astype(np.float64)) <= 2e-6
+    assert rel_l2(outs[1][1], outs[0][1].astype(np.float64)) <= 2e-6
+    sel = [0, 7, 8, 31, 59]
+    assert rel_l2(outs[1][0][:, sel, :], Q.fp_angles(x, sel)) <= TOL
+    for z, yy, xx in (((0, 8), (0, 8), (0, 32)), ((124, 132), (100, 108), (64, 96)), ((250, 256), (248, 256), (224, 256))):
+        assert rel_l2(outs[1][1][z[0]:z[1], yy[0]:yy[1], xx[0]:xx[1]], Q.bp_window(outs[1][0], z, yy, xx)) <= TOL
+    with env(TSP_HOST_PIPELINE_MIN_MB=0, TSP_HOST_CHUNKS=8, TSP_HOST_MEM_CAP_MB=8):
+        P, Q = make(kind, (n, n, n), win, det, vec)
+        with pytest.raises(MemoryError):
+            P.project(B.FP, False, x.ctypes.data, np.zeros(Q.proj_shape, np.float32).ctypes.data, B.MEM_HOST, 0, 0)
+
+
+def test_host_arrays_divided_over_several_gpus():
+    """`ts.astra.set_gpu_index([0, 1, ...])` (the reference's astra.set_gpu_index for ndarray inputs,
+    doc/topics/operator.rst:233-245): tsp_project_multi deals the chunks of the host plan out to the GPUs."""
+    import torch
+
+    import tomosipo_b200 as ts
+
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("needs at least two GPUs")
+    vg = ts.volume(shape=128, size=1)
+    pg = ts.cone(angles=60, shape=(128, 192), size=(1.875, 2.8125), src_orig_dist=4, src_det_dist=6)
+    A = ts.operator(vg, pg)
+    x = np.random.default_rng(8).random(A.domain_shape).astype(np.float32)
+    with env(TSP_HOST_PIPELINE_MIN_MB=0):
+        y1 = A(x)
+        xb1 = A.T(y1)
+        try:
+            ts.astra.set_gpu_index(list(range(ngpu)))
+            y2 = A(x)
+            assert A.astra_projector.info().host_devices == ngpu
+            xb2 = A.T(y1)
+            assert A.astra_projector.info().host_devices == ngpu
+        finally:
+            ts.astra.set_gpu_index(None)
+    assert rel_l2(y2, y1.astype(np.float64)) <= 2e-6
+    assert rel_l2(xb2, xb1.astype(np.float64)) <= 2e-6

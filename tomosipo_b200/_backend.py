@@ -56,6 +56,8 @@ class tsp_projector_info(ctypes.Structure):
         ("fp_uses_transpose", ctypes.c_int32),
         ("fp_uses_tma", ctypes.c_int32),
         ("host_pipelined", ctypes.c_int32),
+        ("host_ring", ctypes.c_int32),
+        ("host_devices", ctypes.c_int32),
     ]
 
 
@@ -73,6 +75,8 @@ EXPORTED_SYMBOLS = (
     "tsp_sirt",
     "tsp_project_fused",
     "tsp_projector_host_plan",
+    "tsp_projector_bp_map",
+    "tsp_project_multi",
 )
 
 
@@ -126,6 +130,11 @@ def lib():
         L.tsp_project_fused.restype = ctypes.c_int
         L.tsp_projector_host_plan.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_int32), ctypes.c_int]
         L.tsp_projector_host_plan.restype = ctypes.c_int
+        L.tsp_project_multi.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.POINTER(ctypes.c_int), ctypes.c_int]
+        L.tsp_project_multi.restype = ctypes.c_int
+        f64p = ctypes.POINTER(ctypes.c_double)
+        L.tsp_projector_bp_map.argtypes = [vp, ctypes.c_int, f64p, f64p]
+        L.tsp_projector_bp_map.restype = ctypes.c_int
         _lib = L
         return _lib
 
@@ -195,6 +204,12 @@ class Projector:
                                  ctypes.c_void_p(proj_ptr), int(batch), int(memory_kind), int(device),
                                  ctypes.c_void_p(stream)))
 
+    def project_multi(self, direction, additive, vol_ptr, proj_ptr, devices):
+        """HOST arrays divided over several GPUs (``astra.set_gpu_index([...])`` in the reference)."""
+        devs = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
+        _check(lib().tsp_project_multi(self._handle, int(direction), int(bool(additive)), ctypes.c_void_p(vol_ptr),
+                                       ctypes.c_void_p(proj_ptr), devs, len(devices)))
+
     def sirt(self, x_ptr, y_ptr, r_ptr, c_ptr, ytmp_ptr, iterations, device=0, stream=0):
         vp = ctypes.c_void_p
         _check(lib().tsp_sirt(self._handle, vp(x_ptr), vp(y_ptr), vp(r_ptr), vp(c_ptr), vp(ytmp_ptr),
@@ -214,6 +229,14 @@ class Projector:
         buf = (ctypes.c_int32 * (4 * max(n, 1)))()
         n = lib().tsp_projector_host_plan(self._handle, int(direction), buf, n)
         return [tuple(buf[4 * k: 4 * k + 4]) for k in range(n)]
+
+    def bp_map(self, angle, xyz):
+        """(U, V, weight) of a world-frame point (x, y, z) on the detector of ``angle`` (host-only)."""
+        p = np.ascontiguousarray(xyz, dtype=np.float64)
+        out = np.zeros(3)
+        f64p = ctypes.POINTER(ctypes.c_double)
+        _check(lib().tsp_projector_bp_map(self._handle, int(angle), p.ctypes.data_as(f64p), out.ctypes.data_as(f64p)))
+        return out
 
     def info(self):
         info = tsp_projector_info()

@@ -110,15 +110,57 @@ def direct_project(projector, vol_link, proj_link, forward=None, additive=False)
         if vol.kind != proj.kind:
             raise ValueError("Cannot project between host and device memory.")
         on_device = vol.kind == "device"
-        projector.project(
-            _backend.FP if forward else _backend.BP,
-            additive,
-            vol.ptr,
-            proj.ptr,
-            _backend.MEM_DEVICE if on_device else _backend.MEM_HOST,
-            device=vol.device if on_device else _default_device(),
-            stream=vol.stream if on_device else 0,
-        )
+        direction = _backend.FP if forward else _backend.BP
+        if on_device:
+            # links of different array libraries pass are_compatible() undetermined: the kernel would then read a
+            # foreign-device pointer, or race with the producer of the other array on its stream
+            if vol.device != proj.device:
+                raise ValueError(
+                    f"Cannot project between arrays on different GPUs (volume on {vol.device}, projections on {proj.device}).")
+            if vol.stream != proj.stream:
+                _order_streams(vol.device, first=proj.stream, then=vol.stream)
+            projector.project(direction, additive, vol.ptr, proj.ptr, _backend.MEM_DEVICE, device=vol.device,
+                              stream=vol.stream)
+            if vol.stream != proj.stream:
+                _order_streams(vol.device, first=vol.stream, then=proj.stream)
+        elif len(_gpu_index) > 1:
+            projector.project_multi(direction, additive, vol.ptr, proj.ptr, _gpu_index)
+        else:
+            projector.project(direction, additive, vol.ptr, proj.ptr, _backend.MEM_HOST,
+                              device=_gpu_index[0] if _gpu_index else _default_device(), stream=0)
+
+
+def _order_streams(device, first, then):
+    """Work submitted to CUDA stream ``then`` from now on runs after what ``first`` holds now (raw stream handles)."""
+    import torch
+
+    with torch.cuda.device(device):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.ExternalStream(first, device=device) if first else torch.cuda.default_stream(device))
+        (torch.cuda.ExternalStream(then, device=device) if then else torch.cuda.default_stream(device)).wait_event(ev)
+
+
+#: GPUs used for HOST arrays; see :func:`set_gpu_index`
+_gpu_index = []
+
+
+def set_gpu_index(gpus):
+    """Choose the GPU(s) that project host (NumPy / CPU tensor) arrays.
+
+    Drop-in for ``astra.set_gpu_index`` as the reference documents it (``doc/topics/operator.rst:226-245``): with a
+    list of several GPUs every projection and backprojection of host arrays is divided over all of them
+    (``tsp_project_multi``); a single index selects that GPU.  Arrays that live on a GPU are always processed where
+    they are.  ``None`` / ``[]`` restores the default (torch's current device, else GPU 0).
+    """
+    global _gpu_index
+    if gpus is None:
+        gpus = []
+    elif isinstance(gpus, (int, np.integer)):
+        gpus = [int(gpus)]
+    gpus = [int(g) for g in gpus]
+    if len(set(gpus)) != len(gpus) or any(g < 0 for g in gpus):
+        raise ValueError(f"Expected a list of distinct, non-negative GPU indices. Got {gpus}")
+    _gpu_index = gpus
 
 
 def _default_device():
@@ -152,7 +194,10 @@ def project(*data, voxel_supersampling=1, detector_supersampling=1, forward=None
     Legacy interface of the reference (``tomosipo/astra.py:221-290``, built on
     ``astra.experimental.do_composite``): every volume is projected onto every
     projection dataset (forward), or every projection dataset is back-projected
-    into every volume (backward); contributions accumulate.
+    into every volume (backward); contributions accumulate.  ``projector``: a
+    pre-built projector (``ts.operator(...).astra_projector``) to use instead
+    of creating one; as in the reference it serves a single volume / projection
+    pair, for which its shapes must match.
     """
     if forward is None:
         raise ValueError("project must be given a forward argument (True/False).")
@@ -160,38 +205,41 @@ def project(*data, voxel_supersampling=1, detector_supersampling=1, forward=None
     projs = [d for d in data if d.is_projection()]
     if not vols or not projs:
         raise ValueError("Expected at least one projection dataset and one volume dataset")
+    if projector is not None and (len(vols) != 1 or len(projs) != 1):
+        raise ValueError("A pre-built projector serves exactly one volume and one projection dataset.")
     targets = projs if forward else vols
     for i, t in enumerate(targets):
         first = not additive
         for s in (vols if forward else projs):
             v, p = (s, t) if forward else (t, s)
-            op = ts.operator(v.geometry, p.geometry, voxel_supersampling=voxel_supersampling,
-                             detector_supersampling=detector_supersampling)
-            direct_project(op.astra_projector, v.link, p.link, forward=forward, additive=not first)
+            proj_handle = projector
+            if proj_handle is None:
+                proj_handle = ts.operator(v.geometry, p.geometry, voxel_supersampling=voxel_supersampling,
+                                          detector_supersampling=detector_supersampling).astra_projector
+            direct_project(proj_handle, v.link, p.link, forward=forward, additive=not first)
             first = False
 
 
-def forward(*data, voxel_supersampling=1, detector_supersampling=1, projector=None):
+def forward(*data, voxel_supersampling=1, detector_supersampling=1, additive=False, projector=None):
     """Legacy forward projection of ``Data`` objects (``tomosipo/astra.py:293-330``)."""
     project(*data, voxel_supersampling=voxel_supersampling, detector_supersampling=detector_supersampling,
-            forward=True, projector=projector)
+            forward=True, additive=additive, projector=projector)
 
 
-def backward(*data, voxel_supersampling=1, detector_supersampling=1, projector=None):
+def backward(*data, voxel_supersampling=1, detector_supersampling=1, additive=False, projector=None):
     """Legacy backprojection of ``Data`` objects (``tomosipo/astra.py:333-371``)."""
     project(*data, voxel_supersampling=voxel_supersampling, detector_supersampling=detector_supersampling,
-            forward=False, projector=projector)
+            forward=False, additive=additive, projector=projector)
 
 
 def fdk(vol_data, proj_data, *, voxel_supersampling=1, detector_supersampling=1):
     """FDK reconstruction of ``proj_data`` into ``vol_data`` (``tomosipo/astra.py:374-406``).
 
-    The reference calls ``astra.experimental.accumulate_FDK``; here: cosine weighting and ramp
-    filter on the GPU (:func:`tomosipo_b200.algorithms.fdk`), then the library's backprojector.
-    The result overwrites the volume dataset's array.
+    The reference calls ``astra.experimental.accumulate_FDK``, which ADDS the reconstruction to the
+    volume dataset's array; so does this (start from zeros for a plain reconstruction).  Cosine
+    weighting and the ramp filter run on the GPU (:func:`tomosipo_b200.algorithms.fdk`), followed by
+    the library's backprojector.
     """
-    import numpy as np
-
     from .algorithms import fdk as _fdk
 
     op = ts.operator(vol_data.geometry, proj_data.geometry, voxel_supersampling=voxel_supersampling,
@@ -199,9 +247,9 @@ def fdk(vol_data, proj_data, *, voxel_supersampling=1, detector_supersampling=1)
     rec = _fdk(op, proj_data.data)
     dst = vol_data.data
     if isinstance(dst, np.ndarray):
-        dst[...] = rec if isinstance(rec, np.ndarray) else rec.cpu().numpy()
+        dst += rec if isinstance(rec, np.ndarray) else rec.cpu().numpy()
     else:
         import torch
 
-        dst.copy_(torch.as_tensor(rec).to(dst.device))
+        dst += torch.as_tensor(rec).to(dst.device)
     return vol_data

@@ -46,7 +46,8 @@ struct BPArgs {
     // register and re-adds it in front of every shared-memory tap (3 extra instructions per update).
     uint32_t magic_off;
     uint32_t magic_off_b;  // same for the alternative pitch
-    int no_rows3;          // tuning aid (TSP_BP_NO_ROWS3): disable the 3-row z-invariant loop
+    int no_rows3;          // tuning aid (TSP_BP_NO_ROWS3): disable the row-sharing z-invariant loops
+    int rows_loop;         // which row-sharing loop z-invariant angles take: 3 = row walk (default), 2 = 3-row pairs (TSP_BP_ROWS)
     // fused SIRT update (tsp_sirt): when set, vol[i] -= epi_mul[i] * value instead of a plain store
     const float *epi_mul;
 };
@@ -96,7 +97,7 @@ __device__ __forceinline__ float bp_sample_global(const float *__restrict__ proj
 // box; shuffles reduce the bounding box; lane 0 writes the local map.
 __device__ __forceinline__ void bp_setup(const BPArgs &P, const BPAngle *__restrict__ ang, int corner,
                                          double xc, double yc, double zc, double hx, double hy,
-                                         double hz, int max_rows, int max_cols, int alt_cols, int u_align, bool allow_rows3, BPLocal *out)
+                                         double hz, int max_rows, int max_cols, int alt_cols, int u_align, bool allow_rows3, int rows_loop, BPLocal *out)
 {
     const double den_c = ang->dn[0] * xc + ang->dn[1] * yc + ang->dn[2] * zc + ang->dn[3];
     const double nu_c = ang->nu[0] * xc + ang->nu[1] * yc + ang->nu[2] * zc + ang->nu[3];
@@ -185,7 +186,8 @@ __device__ __forceinline__ void bp_setup(const BPArgs &P, const BPAngle *__restr
         const double av2 = ang->nv[2] - off_v * ang->dn[2];
         const double dvmax = fabs(av2) / fmin(fabs(dmin), fabs(dmax));
         const bool positive = (av2 >= 0.0) == (den_c > 0.0);
-        if (positive && dvmax <= 0.9999 && wv + 1 <= max_rows) L.z_invariant = 2;
+        // (the row walk reads no spare row)
+        if (positive && dvmax <= 0.9999 && (rows_loop == 3 || wv + 1 <= max_rows)) L.z_invariant = rows_loop;
     }
     L.pad = 0;
     *out = L;
@@ -346,6 +348,60 @@ __device__ __forceinline__ void bp_tile_loop_zinv3(uint32_t sbase, float nu, flo
     }
 }
 
+// Same precondition (z-invariant, 0 <= dv <= 1), walking the detector ROWS instead: voxel i
+// samples rows (j_i, j_i + 1) with j_i - j_{i-1} in {0, 1}, so the only row it can need that the
+// previous voxel did not have is j_i + 1.  h(j) = lerp(p[j][c], p[j][c+1], wu) of that row is
+// formed once (2 taps, one packed lerp per voxel pair) and h(j_i) is selected from the previous
+// voxel's two values: 2 shared-memory taps and 9.5 instructions per voxel instead of 3 / 11.
+// The loop is pitch-agnostic (the row pitch is a register), so one copy serves both TMA variants.
+template <bool CONE, int ZPT>
+__device__ __forceinline__ void bp_tile_loop_rows(uint32_t sbase, uint32_t pitch4, float nu, float nv, float dn, float sv,
+                                                  float wpar, uint32_t magic_off, float (&acc)[ZPT])
+{
+    static_assert(ZPT % 2 == 0, "pairs of voxels");
+    float r = 1.0f, w2 = wpar;
+    if (CONE) { r = rcp_approx(dn); w2 = r * r; }
+    const float fu = nu * r;
+    const float ru = __fadd_rd(fu, BP_MAGIC);
+    const float wu = fu - (ru - BP_MAGIC);
+    const uint32_t cbase = sbase + magic_off + 4u * __float_as_uint(ru);  // row j, column c of the first tap
+    const uint32_t cbase1 = cbase + pitch4;                               // row j + 1
+    const float fv = nv * r;
+    const float dv = sv * r;
+    const float2 M2 = make_float2(BP_MAGIC, BP_MAGIC), NEG1 = make_float2(-1.0f, -1.0f);
+    const float2 wu2 = make_float2(wu, wu), w22 = make_float2(w2, w2), step2 = make_float2(2.0f * dv, 2.0f * dv);
+    float2 fv2 = make_float2(fv, fv + dv);
+    // state carried from voxel i - 1: its row index (as magic-float bits) and h of its two rows
+    const float rv0 = __fadd_rd(fv, BP_MAGIC);
+    uint32_t prev = __float_as_uint(rv0);
+    float h0p, h1p;
+    {
+        const uint32_t a = prev * pitch4 + cbase;
+        const float t0 = lds_f32<0>(a), t1 = lds_f32<4>(a);
+        h0p = fmaf(wu, t1 - t0, t0);
+        h1p = h0p;
+    }
+#pragma unroll
+    for (int i = 0; i < ZPT; i += 2) {
+        const float2 rv2 = __fadd2_rd(fv2, M2);
+        const float2 wv2 = __fadd2_rn(fv2, __ffma2_rn(rv2, NEG1, M2));
+        const uint32_t bx = __float_as_uint(rv2.x), by = __float_as_uint(rv2.y);
+        const uint32_t a0 = bx * pitch4 + cbase1, a1 = by * pitch4 + cbase1;
+        const float2 q0 = make_float2(lds_f32<0>(a0), lds_f32<0>(a1));
+        const float2 q1 = make_float2(lds_f32<4>(a0), lds_f32<4>(a1));
+        const float2 hn = __ffma2_rn(wu2, __ffma2_rn(q0, NEG1, q1), q0);  // h(j_i + 1), h(j_{i+1} + 1)
+        float2 hl;                                                        // h(j_i), h(j_{i+1})
+        hl.x = (bx != prev) ? h1p : h0p;
+        hl.y = (by != bx) ? hn.x : hl.x;
+        const float2 d = __ffma2_rn(hl, NEG1, hn);
+        const float2 val = __ffma2_rn(wv2, d, hl);
+        const float2 a2 = __ffma2_rn(w22, val, make_float2(acc[i], acc[i + 1]));
+        acc[i] = a2.x; acc[i + 1] = a2.y;
+        prev = by; h0p = hl.y; h1p = hn.y;
+        fv2 = __fadd2_rn(fv2, step2);
+    }
+}
+
 // One angle's contribution to a thread's z run.  `L` lives in shared memory;
 // `sbase` is the shared byte address of the staged footprint (row pitch PITCH).
 template <bool CONE, int ZPT, int PITCH, int PITCH_B>
@@ -360,7 +416,11 @@ __device__ __forceinline__ void bp_accumulate_angle(const BPArgs &P, const BPLoc
     float dn = CONE ? fmaf(L.ad[0], dx, fmaf(L.ad[1], dy, fmaf(L.ad[2], dz0, L.bd))) : 1.0f;
     const float su = L.au[2], sv = L.av[2], sd = L.ad[2];
     const float wpar = L.weight;
-    if (mode == BP_SMEM) {
+    if (ZPT % 2 == 0 && L.z_invariant == 3) {  // only ever set for BP_SMEM / BP_SMEM_B
+        const bool b = PITCH_B != PITCH && mode == BP_SMEM_B;
+        bp_tile_loop_rows<CONE, (ZPT % 2 == 0 ? ZPT : 2)>(sbase, b ? 4u * PITCH_B : 4u * PITCH, nu, nv, dn, sv, wpar, b ? P.magic_off_b : P.magic_off,
+                                                          reinterpret_cast<float (&)[(ZPT % 2 == 0 ? ZPT : 2)]>(acc));
+    } else if (mode == BP_SMEM) {
         if (ZPT % 2 == 0 && L.z_invariant == 2) bp_tile_loop_zinv3<CONE, (ZPT % 2 == 0 ? ZPT : 2), PITCH>(sbase, nu, nv, dn, sv, wpar, P.magic_off, reinterpret_cast<float (&)[(ZPT % 2 == 0 ? ZPT : 2)]>(acc));
         else if (L.z_invariant) bp_tile_loop_zinv<CONE, ZPT, PITCH>(sbase, nu, nv, dn, sv, wpar, P.magic_off, acc);
         else bp_tile_loop<CONE, false, ZPT, PITCH>(sbase, nu, nv, dn, su, sv, sd, 0.0f, 0.0f, wpar, P.magic_off, acc);
@@ -438,7 +498,7 @@ __global__ void __launch_bounds__(BP_THREADS) bp_kernel(const BPArgs P)
             const int j = tid >> 3;
             // clamp so that all 8 lanes of a group take part in the shuffles
             const int a = a0 + min(j, na - 1);
-            bp_setup(P, P.angles + a, tid & 7, xc, yc, zc, hx, hy, hz, BP_WV, BP_WU, 0, 1, false, &loc[j]);
+            bp_setup(P, P.angles + a, tid & 7, xc, yc, zc, hx, hy, hz, BP_WV, BP_WU, 0, 1, false, 0, &loc[j]);
         }
         __syncthreads();
         // stage footprints: warps over rows, lanes over columns
@@ -490,7 +550,7 @@ constexpr int BP_TMA_THREADS = BP_TMA_CONSUMERS + 32;
 #ifndef BP_TMA_STAGES_Z32
 #define BP_TMA_STAGES_Z32 4  // ring depth at 32 voxels per thread (tuning: -DBP_TMA_STAGES_Z32=n)
 #endif
-__host__ __device__ constexpr int bp_tma_stages(int zpt) { return zpt >= 32 ? BP_TMA_STAGES_Z32 : (zpt >= 16 ? 6 : 8); }
+__host__ __device__ constexpr int bp_tma_stages(int zpt) { return zpt >= 32 ? BP_TMA_STAGES_Z32 : (zpt >= 24 ? 4 : (zpt >= 16 ? 6 : 8)); }
 __host__ __device__ constexpr size_t bp_tma_box_bytes(int zpt) { return (size_t)bp_wv(zpt) * BP_TMA_PITCH * 4; }
 // ring stages are 128-byte aligned (TMA destination alignment)
 __host__ __device__ constexpr size_t bp_tma_stage_bytes(int zpt) { return (bp_tma_box_bytes(zpt) + 127) / 128 * 128; }
@@ -584,10 +644,13 @@ bp_tma_kernel(const BPArgs P, const __grid_constant__ TensorMapPair tmaps)  // m
         const int group = lane >> 3, corner = lane & 7;
         int s = 0;
         uint32_t parity = 1u;  // waiting on a fresh "empty" barrier with parity 1 passes at once
+        BPLocal L;
         for (int a0 = 0; a0 < P.n_angles; a0 += 4) {
             const int a = min(a0 + group, P.n_angles - 1);
-            BPLocal L;
-            bp_setup(P, P.angles + a, corner, xc, yc, zc, hx, hy, hz, WV, BP_TMA_PITCH, BP_TMA_PITCH_B, 4, !P.no_rows3, &L);  // valid in corner-0 lanes
+#ifdef BP_EXP_NOSETUP
+            if (a0 == 0)  // experiment: the set-up of the first four angles serves every angle (wrong results)
+#endif
+            bp_setup(P, P.angles + a, corner, xc, yc, zc, hx, hy, hz, WV, BP_TMA_PITCH, BP_TMA_PITCH_B, 4, !P.no_rows3, P.rows_loop, &L);  // valid in corner-0 lanes
             for (int g = 0; g < 4 && a0 + g < P.n_angles; ++g) {
                 const int angle = a0 + g;
                 mbar_wait(empty + 8u * s, parity);
@@ -626,7 +689,9 @@ bp_tma_kernel(const BPArgs P, const __grid_constant__ TensorMapPair tmaps)  // m
     int s = 0;
     uint32_t parity = 0u;
     for (int angle = 0; angle < P.n_angles; ++angle) {
+#ifndef BP_EXP_NOWAIT
         mbar_wait(full + 8u * s, parity);
+#endif
         if (in_xy)
             bp_accumulate_angle<CONE, ZPT, BP_TMA_PITCH, BP_TMA_PITCH_B>(P, loc[s], bufs + (uint32_t)s * STAGE_BYTES, angle, dx, dy, dz0,
                                                          row_pitch, acc);

@@ -65,6 +65,8 @@ struct DeviceState {
     std::vector<size_t> list_offset;
     // host-array pipeline (tsp_project with TSP_MEM_HOST): copy-in / copy-out streams
     cudaStream_t s_in = nullptr, s_out = nullptr;
+    // private stream-ordered memory pool of this (projector, device): per-call scratch and host-array staging
+    cudaMemPool_t pool = nullptr;
 };
 
 }  // namespace tsp
@@ -94,4 +96,6 @@ struct tsp_projector {
     std::vector<HostChunk> host_bp, host_fp;
     bool host_planned = false;
     std::atomic<int> host_pipelined{0};  // last host-array call ran the chunked pipeline
+    std::atomic<int> host_ring{0};       // ... out of the bounded ring of chunk buffers (device memory budget exceeded)
+    std::atomic<int> host_devices{0};    // ... on this many devices
 };

@@ -7,11 +7,14 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
+#include <climits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <thread>
 
 #include "bp_kernels.cuh"
 #include "fp_kernels.cuh"
@@ -338,6 +341,7 @@ static void free_device_state(tsp_projector *pr)
         cudaFree(kv.second.bp_angles);
         if (kv.second.s_in) cudaStreamDestroy(kv.second.s_in);
         if (kv.second.s_out) cudaStreamDestroy(kv.second.s_out);
+        if (kv.second.pool) cudaMemPoolDestroy(kv.second.pool);
     }
     cudaSetDevice(cur);
     pr->dev.clear();
@@ -370,6 +374,8 @@ extern "C" int tsp_projector_get_info(const tsp_projector *pr, tsp_projector_inf
     info->fp_uses_transpose = pr->fp_uses_transpose;
     info->fp_uses_tma = pr->fp_uses_tma;
     info->host_pipelined = pr->host_pipelined;
+    info->host_ring = pr->host_ring;
+    info->host_devices = pr->host_devices;
     return TSP_OK;
 }
 
@@ -377,6 +383,20 @@ extern "C" int tsp_projector_marching_axes(const tsp_projector *pr, int32_t *axe
 {
     if (!pr || !axes) return fail(TSP_ERR_INVALID, "NULL argument");
     for (size_t i = 0; i < pr->march_axis.size(); ++i) axes[i] = pr->march_axis[i];
+    return TSP_OK;
+}
+
+extern "C" int tsp_projector_bp_map(const tsp_projector *pr, int angle, const double *xyz, double *out)
+{
+    if (!pr || !xyz || !out) return fail(TSP_ERR_INVALID, "NULL argument");
+    if (angle < 0 || angle >= pr->g.n_angles) return fail(TSP_ERR_INVALID, "angle %d out of range", angle);
+    const BPAngle &m = pr->bp_angles[angle];
+    double x[3];
+    for (int i = 0; i < 3; ++i) x[i] = (xyz[i] - 0.5 * (pr->g.win_min[i] + pr->g.win_max[i])) / pr->sigma[i];
+    const double den = m.dn[0] * x[0] + m.dn[1] * x[1] + m.dn[2] * x[2] + m.dn[3];
+    out[0] = (m.nu[0] * x[0] + m.nu[1] * x[1] + m.nu[2] * x[2] + m.nu[3]) / den;
+    out[1] = (m.nv[0] * x[0] + m.nv[1] * x[1] + m.nv[2] * x[2] + m.nv[3]) / den;
+    out[2] = pr->g.kind == TSP_KIND_CONE_VEC ? 1.0 / (den * den) : m.weight;
     return TSP_OK;
 }
 
@@ -422,16 +442,45 @@ static int get_device_state(tsp_projector *pr, int device, DeviceState **out)
     }
     CUDA_TRY(cudaMalloc(&st.fp_pairs, std::max<size_t>(1, pairs.size()) * sizeof(int)));
     CUDA_TRY(cudaMemcpy(st.fp_pairs, pairs.data(), pairs.size() * sizeof(int), cudaMemcpyHostToDevice));
-    // keep freed scratch (the transposed volume copy) cached in the pool
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        uint64_t keep = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    // private pool: caches one transposed-volume scratch between calls, nothing more (see pool_alloc)
+    {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&st.pool, &props) == cudaSuccess) {
+            const int ny_pad = (pr->g.ny + 3) / 4 * 4;
+            uint64_t keep = (uint64_t)pr->g.nz * pr->g.nx * ny_pad * sizeof(float);
+            if (const char *e = getenv("TSP_POOL_KEEP_MB")) keep = (uint64_t)std::max(0LL, atoll(e)) << 20;
+            cudaMemPoolSetAttribute(st.pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        } else {
+            cudaGetLastError();
+            st.pool = nullptr;  // falls back to the device's default pool, untouched
+        }
     }
     *out = &(pr->dev[device] = st);
     return TSP_OK;
 }
 
+
+// ---- device memory of a call: a private stream-ordered pool per (projector, device) ------------------
+// The default pool is left alone (raising its release threshold is a process-wide side effect
+// and keeps memory away from other allocators).  The private pool keeps at most `keep` bytes cached between
+// calls - enough for the per-call scratch of an iterative loop (the transposed volume copy of launch_fp) -
+// and hands everything above that back to the driver at the next synchronisation point.
+static cudaError_t pool_alloc(DeviceState *st, void **p, size_t bytes, cudaStream_t stream)
+{
+    if (st->pool) return cudaMallocFromPoolAsync(p, bytes, st->pool, stream);
+    return cudaMallocAsync(p, bytes, stream);
+}
+
+// Per-call scratch from the projector's private pool, released (stream-ordered) on every exit path.
+struct PoolScratch {
+    void *p = nullptr;
+    cudaStream_t stream = nullptr;
+    ~PoolScratch() { if (p) cudaFreeAsync(p, stream); }
+};
 
 // defined in the TMA section below
 static bool make_tensor_map_3d(const float *base, const uint64_t dims[3], const uint64_t stride_bytes[2],
@@ -473,11 +522,22 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
 
     bool need_t = false;
     for (const FPGroup &grp : pr->groups) need_t |= grp.transposed;
+    // the transpose grid covers nz * batch planes: a batch too tall for it goes item by item
+    if (need_t && batch > 1 && (long long)g.nz * batch > 65535) {
+        for (int b = 0; b < batch; ++b)
+            if (int rc = launch_fp(pr, st, vol + b * nvox, proj + b * npix, additive, stream,
+                                   epi_sub ? epi_sub + b * npix : nullptr, epi_mul ? epi_mul + b * npix : nullptr, 1))
+                return rc;
+        return TSP_OK;
+    }
+    if (need_t && g.nz > 65535) return fail(TSP_ERR_INVALID, "nz exceeds the transpose grid");
     float *vol_t = nullptr;
+    PoolScratch scratch;
     const int ny_pad = (g.ny + 3) / 4 * 4;  // row pitch of the transposed copy: whole 16-byte units (TMA stride rule)
     if (need_t) {
-        CUDA_TRY(cudaMallocAsync(&vol_t, (size_t)batch * g.nz * g.nx * ny_pad * sizeof(float), stream));
-        if ((long long)g.nz * batch > 65535) return fail(TSP_ERR_INVALID, "nz * batch exceeds the transpose grid");
+        CUDA_TRY(pool_alloc(st, &scratch.p, (size_t)batch * g.nz * g.nx * ny_pad * sizeof(float), stream));
+        scratch.stream = stream;
+        vol_t = (float *)scratch.p;
         dim3 grid((g.nx + 31) / 32, (g.ny + 31) / 32, g.nz * batch), block(32, 8);  // batch items are contiguous planes
         transpose_xy_kernel<<<grid, block, 0, stream>>>(vol, vol_t, g.nx, g.ny, ny_pad);
         ++pr->launches;
@@ -612,7 +672,6 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
         }
     }
     pr->fp_uses_tma = used_tma;
-    if (vol_t) CUDA_TRY(cudaFreeAsync(vol_t, stream));
     CUDA_TRY(cudaGetLastError());
     return TSP_OK;
 }
@@ -624,7 +683,7 @@ static int bp_zpt_choice(int nx, int ny, int nz)
 {
     if (const char *e = getenv("TSP_BP_ZPT")) {
         const int v = atoi(e);
-        if (v == 1 || v == 4 || v == 8 || v == 16 || v == 32) return v;
+        if (v == 1 || v == 4 || v == 8 || v == 16 || v == 24 || v == 32) return v;
     }
     // longest run that (a) is not mostly padding and (b) still leaves >= 4 CTAs per SM to balance
     const int cand[5] = {32, 16, 8, 4, 1};
@@ -751,6 +810,7 @@ static int launch_bp_tma_variant(bool cone, int zpt, dim3 grid, cudaStream_t str
         TSP_BP_CASE(4)
         TSP_BP_CASE(8)
         TSP_BP_CASE(16)
+        TSP_BP_CASE(24)
         TSP_BP_CASE(32)
     }
 #undef TSP_BP_CASE
@@ -785,6 +845,8 @@ static int launch_bp(tsp_projector *pr, DeviceState *st, float *vol, const float
     P.magic_off = 0;
     P.magic_off_b = 0;
     P.no_rows3 = getenv("TSP_BP_NO_ROWS3") ? 1 : 0;
+    P.rows_loop = 3;
+    if (const char *e = getenv("TSP_BP_ROWS")) P.rows_loop = atoi(e) == 2 ? 2 : 3;
     P.epi_mul = epi_mul;
     const bool cone = g.kind == TSP_KIND_CONE_VEC;
     int used_tma = 0;
@@ -1071,99 +1133,232 @@ extern "C" int tsp_projector_host_plan(tsp_projector *pr, int direction, int32_t
     return (int)chunks.size();
 }
 
-// One FP (SET) or BP (SET) between host arrays, chunked and pipelined over three streams.
-static int project_host_pipelined(tsp_projector *pr, DeviceState *st, int device, int direction, float *vol, float *proj,
-                                  cudaStream_t stream)
+// Everything a host-array call acquires on one device; released on every exit path.
+struct PipeResources {
+    cudaStream_t stream = nullptr;  // the stream the buffers are allocated / freed on
+    std::vector<void *> bufs;
+    std::vector<cudaEvent_t> events;
+    cudaStream_t own_stream = nullptr;
+    ~PipeResources()
+    {
+        for (void *b : bufs) cudaFreeAsync(b, stream);
+        if (stream || !bufs.empty()) cudaStreamSynchronize(stream);
+        for (cudaEvent_t e : events) cudaEventDestroy(e);
+        if (own_stream) cudaStreamDestroy(own_stream);
+    }
+    cudaError_t alloc(DeviceState *st, float **p, size_t n_floats)
+    {
+        void *q = nullptr;
+        cudaError_t e = pool_alloc(st, &q, std::max<size_t>(n_floats, 1) * sizeof(float), stream);
+        if (e == cudaSuccess) { bufs.push_back(q); *p = (float *)q; }
+        return e;
+    }
+    cudaError_t event(cudaEvent_t *ev)
+    {
+        cudaError_t e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming);
+        if (e == cudaSuccess) events.push_back(*ev);
+        return e;
+    }
+};
+
+// Device-memory budget of a host-array call, in bytes (0 = unlimited): TSP_HOST_MEM_CAP_MB, else what the device
+// has free minus a reserve.  Above it the pipeline runs out of a ring of chunk buffers instead of whole arrays.
+static size_t host_mem_cap()
+{
+    if (const char *e = getenv("TSP_HOST_MEM_CAP_MB")) return (size_t)std::max(1LL, atoll(e)) << 20;
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return fr - std::min(fr / 8, (size_t)4 << 30);
+}
+
+// One FP (SET) or BP (SET) between host arrays on ONE device, over the chunks `order` (indices into the plan):
+// H2D(k+1) | kernels(k) | D2H(k-1) on three streams.
+//   input axis  = detector rows for BP, volume slices for FP   (what a chunk reads;  unit = one row / one slice)
+//   output axis = volume slices for BP, detector rows for FP   (what a chunk writes, disjoint between chunks)
+// Two memory modes:
+//   range mode (default): one input and one output buffer spanning the union of the chunks' ranges; an input
+//       row / slice is uploaded once, by the first chunk that needs it;
+//   ring mode (when range mode would exceed `cap` bytes): RING input and RING output buffers of the largest
+//       chunk's size; every chunk uploads its whole input range (neighbouring chunks' inputs overlap, so up to
+//       ~2x the upload traffic), and a buffer is reused once the chunk that held it has finished with it.
+//       Device memory is then bounded by 3 x (largest chunk input + output) whatever the size of the arrays -
+//       the out-of-core path of ASTRA's CompositeGeometryManager (reference doc/topics/operator.rst:226-261).
+static int project_host_chunks(tsp_projector *pr, int device, int direction, float *vol, float *proj,
+                               const std::vector<int> &order, cudaStream_t user_stream, size_t cap, bool *used_ring)
 {
     const tsp_geometry &g = pr->g;
-    const size_t nvox = (size_t)g.nx * g.ny * g.nz, npix = (size_t)g.det_rows * g.n_angles * g.det_cols;
     const size_t row = (size_t)g.n_angles * g.det_cols, slice = (size_t)g.nx * g.ny;
+    const bool fp = direction == TSP_FP;
+    const std::vector<tsp_projector::HostChunk> &chunks = fp ? pr->host_fp : pr->host_bp;
+    const size_t in_unit = fp ? slice : row, out_unit = fp ? row : slice;
+    float *const host_in = fp ? vol : proj, *const host_out = fp ? proj : vol;
+    auto in0 = [&](const tsp_projector::HostChunk &c) { return fp ? c.z0 : c.v0; };
+    auto in1 = [&](const tsp_projector::HostChunk &c) { return fp ? c.z1 : c.v1; };
+    auto out0 = [&](const tsp_projector::HostChunk &c) { return fp ? c.v0 : c.z0; };
+    auto out1 = [&](const tsp_projector::HostChunk &c) { return fp ? c.v1 : c.z1; };
+    if (order.empty()) return TSP_OK;
+
+    DeviceState *st = nullptr;
+    if (int rc = get_device_state(pr, device, &st)) return rc;
     if (!st->s_in) CUDA_TRY(cudaStreamCreateWithFlags(&st->s_in, cudaStreamNonBlocking));
     if (!st->s_out) CUDA_TRY(cudaStreamCreateWithFlags(&st->s_out, cudaStreamNonBlocking));
-    float *dvol = nullptr, *dproj = nullptr;
-    CUDA_TRY(cudaMallocAsync(&dvol, nvox * sizeof(float), stream));
-    CUDA_TRY(cudaMallocAsync(&dproj, npix * sizeof(float), stream));
-    const std::vector<tsp_projector::HostChunk> &chunks = direction == TSP_FP ? pr->host_fp : pr->host_bp;
-    std::vector<cudaEvent_t> ev_in(chunks.size()), ev_done(chunks.size());
-    cudaEvent_t ev_start;
-    CUDA_TRY(cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming));
-    for (size_t k = 0; k < chunks.size(); ++k) {
-        CUDA_TRY(cudaEventCreateWithFlags(&ev_in[k], cudaEventDisableTiming));
-        CUDA_TRY(cudaEventCreateWithFlags(&ev_done[k], cudaEventDisableTiming));
+
+    int lo_in = INT_MAX, hi_in = 0, lo_out = INT_MAX, hi_out = 0, max_in = 0, max_out = 0;
+    for (int k : order) {
+        const auto &c = chunks[k];
+        lo_in = std::min(lo_in, in0(c)); hi_in = std::max(hi_in, in1(c));
+        lo_out = std::min(lo_out, out0(c)); hi_out = std::max(hi_out, out1(c));
+        max_in = std::max(max_in, in1(c) - in0(c)); max_out = std::max(max_out, out1(c) - out0(c));
     }
+    const size_t range_bytes = ((size_t)(hi_in - lo_in) * in_unit + (size_t)(hi_out - lo_out) * out_unit) * sizeof(float);
+    const bool ring = cap != 0 && range_bytes > cap;
+    constexpr int RING = 3;
+    if (used_ring) *used_ring = ring;
+    if (ring && (size_t)RING * ((size_t)max_in * in_unit + (size_t)max_out * out_unit) * sizeof(float) > cap)
+        return fail(TSP_ERR_NOMEM, "host-array pipeline: %d ring buffers of the largest chunk (%zu MB) exceed the device memory budget of %zu MB; "
+                    "raise TSP_HOST_CHUNKS", RING, ((size_t)max_in * in_unit + (size_t)max_out * out_unit) * sizeof(float) >> 20, cap >> 20);
+
+    PipeResources res;
+    res.stream = user_stream;
+    float *din[RING] = {nullptr, nullptr, nullptr}, *dout[RING] = {nullptr, nullptr, nullptr};
+    const int nbuf = ring ? RING : 1;
+    for (int i = 0; i < nbuf; ++i) {
+        CUDA_TRY(res.alloc(st, &din[i], (size_t)(ring ? max_in : hi_in - lo_in) * in_unit));
+        CUDA_TRY(res.alloc(st, &dout[i], (size_t)(ring ? max_out : hi_out - lo_out) * out_unit));
+    }
+    const size_t n = order.size();
+    std::vector<cudaEvent_t> ev_in(n), ev_done(n), ev_out(n);
+    cudaEvent_t ev_start;
+    CUDA_TRY(res.event(&ev_start));
+    for (size_t i = 0; i < n; ++i) {
+        CUDA_TRY(res.event(&ev_in[i]));
+        CUDA_TRY(res.event(&ev_done[i]));
+        CUDA_TRY(res.event(&ev_out[i]));
+    }
+    cudaStream_t stream = user_stream;
     CUDA_TRY(cudaEventRecord(ev_start, stream));  // buffers allocated, earlier work on `stream` ordered before us
     CUDA_TRY(cudaStreamWaitEvent(st->s_in, ev_start, 0));
     CUDA_TRY(cudaStreamWaitEvent(st->s_out, ev_start, 0));
-    int rc = TSP_OK;
-    if (direction == TSP_FP) {
-        std::vector<char> uploaded(g.nz, 0);
-        for (size_t k = 0; k < chunks.size() && rc == TSP_OK; ++k) {
-            const auto &c = chunks[k];
-            // upload the slices of this block's z range that no earlier block brought in (maximal runs)
-            for (int z = c.z0; z < c.z1;) {
-                if (uploaded[z]) { ++z; continue; }
-                int e = z;
-                while (e < c.z1 && !uploaded[e]) uploaded[e++] = 1;
-                CUDA_TRY(cudaMemcpyAsync(dvol + (size_t)z * slice, vol + (size_t)z * slice, (size_t)(e - z) * slice * sizeof(float),
-                                         cudaMemcpyHostToDevice, st->s_in));
-                z = e;
+
+    std::vector<char> uploaded(ring ? 0 : (size_t)(hi_in - lo_in), 0);
+    for (size_t i = 0; i < n; ++i) {
+        const auto &c = chunks[order[i]];
+        const int slot = ring ? (int)(i % RING) : 0;
+        // base pointers such that element (unit u of the full array) lives at base + u * unit
+        float *in_base = ring ? din[slot] - (size_t)in0(c) * in_unit : din[0] - (size_t)lo_in * in_unit;
+        float *out_base = ring ? dout[slot] - (size_t)out0(c) * out_unit : dout[0] - (size_t)lo_out * out_unit;
+        if (ring) {
+            // the slot's previous tenant (chunk i - RING) must be done: its kernels with the input buffer ...
+            if (i >= RING) CUDA_TRY(cudaStreamWaitEvent(st->s_in, ev_done[i - RING], 0));
+            CUDA_TRY(cudaMemcpyAsync(in_base + (size_t)in0(c) * in_unit, host_in + (size_t)in0(c) * in_unit,
+                                     (size_t)(in1(c) - in0(c)) * in_unit * sizeof(float), cudaMemcpyHostToDevice, st->s_in));
+        } else {
+            // upload what no earlier chunk brought in (maximal runs)
+            for (int u = in0(c); u < in1(c);) {
+                if (uploaded[u - lo_in]) { ++u; continue; }
+                int e = u;
+                while (e < in1(c) && !uploaded[e - lo_in]) uploaded[e++ - lo_in] = 1;
+                CUDA_TRY(cudaMemcpyAsync(in_base + (size_t)u * in_unit, host_in + (size_t)u * in_unit,
+                                         (size_t)(e - u) * in_unit * sizeof(float), cudaMemcpyHostToDevice, st->s_in));
+                u = e;
             }
-            CUDA_TRY(cudaEventRecord(ev_in[k], st->s_in));
-            CUDA_TRY(cudaStreamWaitEvent(stream, ev_in[k], 0));
-            DeviceState *sst = nullptr;
-            if ((rc = get_device_state(c.sub, device, &sst))) break;
-            const int64_t l0 = c.sub->launches;
-            rc = launch_fp(c.sub, sst, dvol + (size_t)c.z0 * slice, dproj + (size_t)c.v0 * row, 0, stream);
-            pr->launches += c.sub->launches - l0;
-            pr->fp_uses_tma = c.sub->fp_uses_tma.load(); pr->fp_uses_transpose = c.sub->fp_uses_transpose.load();
-            if (rc) break;
-            CUDA_TRY(cudaEventRecord(ev_done[k], stream));
-            CUDA_TRY(cudaStreamWaitEvent(st->s_out, ev_done[k], 0));
-            CUDA_TRY(cudaMemcpyAsync(proj + (size_t)c.v0 * row, dproj + (size_t)c.v0 * row,
-                                     (size_t)(c.v1 - c.v0) * row * sizeof(float), cudaMemcpyDeviceToHost, st->s_out));
         }
-    } else {
-        std::vector<char> uploaded(g.det_rows, 0);
-        for (size_t k = 0; k < chunks.size() && rc == TSP_OK; ++k) {
-            const auto &c = chunks[k];
-            // upload the rows of this chunk that no earlier chunk brought in (maximal runs)
-            for (int v = c.v0; v < c.v1;) {
-                if (uploaded[v]) { ++v; continue; }
-                int e = v;
-                while (e < c.v1 && !uploaded[e]) uploaded[e++] = 1;
-                CUDA_TRY(cudaMemcpyAsync(dproj + (size_t)v * row, proj + (size_t)v * row, (size_t)(e - v) * row * sizeof(float),
-                                         cudaMemcpyHostToDevice, st->s_in));
-                v = e;
-            }
-            CUDA_TRY(cudaEventRecord(ev_in[k], st->s_in));
-            CUDA_TRY(cudaStreamWaitEvent(stream, ev_in[k], 0));
-            DeviceState *sst = nullptr;
-            if ((rc = get_device_state(c.sub, device, &sst))) break;
-            const int64_t l0 = c.sub->launches;
-            rc = launch_bp(c.sub, sst, dvol + (size_t)c.z0 * slice, dproj + (size_t)c.v0 * row, 0, stream);
-            pr->launches += c.sub->launches - l0;
-            pr->bp_uses_tma = c.sub->bp_uses_tma.load();
-            if (rc) break;
-            CUDA_TRY(cudaEventRecord(ev_done[k], stream));
-            CUDA_TRY(cudaStreamWaitEvent(st->s_out, ev_done[k], 0));
-            CUDA_TRY(cudaMemcpyAsync(vol + (size_t)c.z0 * slice, dvol + (size_t)c.z0 * slice,
-                                     (size_t)(c.z1 - c.z0) * slice * sizeof(float), cudaMemcpyDeviceToHost, st->s_out));
-        }
+        CUDA_TRY(cudaEventRecord(ev_in[i], st->s_in));
+        CUDA_TRY(cudaStreamWaitEvent(stream, ev_in[i], 0));
+        // ... and its download out of the output buffer
+        if (ring && i >= RING) CUDA_TRY(cudaStreamWaitEvent(stream, ev_out[i - RING], 0));
+        DeviceState *sst = nullptr;
+        if (int rc = get_device_state(c.sub, device, &sst)) return rc;
+        const int64_t l0 = c.sub->launches;
+        float *dvol_c = fp ? in_base + (size_t)c.z0 * slice : out_base + (size_t)c.z0 * slice;
+        float *dproj_c = fp ? out_base + (size_t)c.v0 * row : in_base + (size_t)c.v0 * row;
+        int rc = fp ? launch_fp(c.sub, sst, dvol_c, dproj_c, 0, stream) : launch_bp(c.sub, sst, dvol_c, dproj_c, 0, stream);
+        pr->launches += c.sub->launches - l0;
+        if (fp) { pr->fp_uses_tma = c.sub->fp_uses_tma.load(); pr->fp_uses_transpose = c.sub->fp_uses_transpose.load(); }
+        else pr->bp_uses_tma = c.sub->bp_uses_tma.load();
+        if (rc) return rc;
+        CUDA_TRY(cudaEventRecord(ev_done[i], stream));
+        CUDA_TRY(cudaStreamWaitEvent(st->s_out, ev_done[i], 0));
+        CUDA_TRY(cudaMemcpyAsync(host_out + (size_t)out0(c) * out_unit, out_base + (size_t)out0(c) * out_unit,
+                                 (size_t)(out1(c) - out0(c)) * out_unit * sizeof(float), cudaMemcpyDeviceToHost, st->s_out));
+        CUDA_TRY(cudaEventRecord(ev_out[i], st->s_out));
     }
-    // the user's stream completes after the copy-out stream; then everything is released
-    cudaEvent_t ev_out;
-    CUDA_TRY(cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming));
-    CUDA_TRY(cudaEventRecord(ev_out, st->s_out));
-    CUDA_TRY(cudaStreamWaitEvent(stream, ev_out, 0));
-    cudaFreeAsync(dvol, stream);
-    cudaFreeAsync(dproj, stream);
-    cudaError_t e = cudaStreamSynchronize(stream);
-    cudaStreamSynchronize(st->s_in);
-    for (size_t k = 0; k < chunks.size(); ++k) { cudaEventDestroy(ev_in[k]); cudaEventDestroy(ev_done[k]); }
-    cudaEventDestroy(ev_start);
-    cudaEventDestroy(ev_out);
-    if (rc == TSP_OK && e != cudaSuccess) return fail(TSP_ERR_CUDA, "host pipeline failed: %s", cudaGetErrorString(e));
+    // the user's stream completes after the copy-out stream; the destructor of `res` then releases everything
+    CUDA_TRY(cudaStreamWaitEvent(stream, ev_out[n - 1], 0));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    CUDA_TRY(cudaStreamSynchronize(st->s_in));
+    return TSP_OK;
+}
+
+static int project_host_pipelined(tsp_projector *pr, int device, int direction, float *vol, float *proj, cudaStream_t stream)
+{
+    const std::vector<tsp_projector::HostChunk> &chunks = direction == TSP_FP ? pr->host_fp : pr->host_bp;
+    std::vector<int> order(chunks.size());
+    for (size_t k = 0; k < chunks.size(); ++k) order[k] = (int)k;
+    bool ring = false;
+    const int rc = project_host_chunks(pr, device, direction, vol, proj, order, stream, host_mem_cap(), &ring);
+    pr->host_ring = ring ? 1 : 0;
     return rc;
+}
+
+// Host arrays over several devices - what `astra.set_gpu_index([0, 1, ...])` switches on in the reference
+// (doc/topics/operator.rst:233-245): the chunks of the plan are independent sub-problems with disjoint outputs, so
+// each device takes a contiguous run of them (contiguous in the output axis: neighbouring chunks share input rows /
+// slices) and runs the single-device pipeline over its share from its own host thread.
+extern "C" int tsp_project_multi(tsp_projector *pr, int direction, int additive, void *vol, void *proj, const int *devices,
+                                 int n_devices)
+{
+    if (!pr) return fail(TSP_ERR_INVALID, "projector is NULL");
+    if (!vol || !proj) return fail(TSP_ERR_INVALID, "vol / proj pointer is NULL");
+    if (direction != TSP_FP && direction != TSP_BP) return fail(TSP_ERR_INVALID, "direction must be TSP_FP or TSP_BP");
+    if (!devices || n_devices < 1) return fail(TSP_ERR_INVALID, "need at least one device");
+    const int ndev = tsp_device_count();
+    if (ndev == 0) return fail(TSP_ERR_CUDA, "no CUDA device available (libtsproj has no CPU fallback)");
+    for (int i = 0; i < n_devices; ++i) {
+        if (devices[i] < 0 || devices[i] >= ndev) return fail(TSP_ERR_INVALID, "device %d out of range [0, %d)", devices[i], ndev);
+        for (int j = 0; j < i; ++j)
+            if (devices[j] == devices[i]) return fail(TSP_ERR_INVALID, "device %d listed twice", devices[i]);
+    }
+    // additive calls, small problems and single-device lists take the ordinary path on the first device
+    if (n_devices == 1 || additive || !plan_host_pipeline(pr))
+        return tsp_project(pr, direction, additive, vol, proj, 1, TSP_MEM_HOST, devices[0], nullptr);
+    const std::vector<tsp_projector::HostChunk> &chunks = direction == TSP_FP ? pr->host_fp : pr->host_bp;
+    // chunks sorted along the output axis, cut into n_devices contiguous shares of (nearly) equal output size
+    std::vector<int> sorted(chunks.size());
+    for (size_t k = 0; k < chunks.size(); ++k) sorted[k] = (int)k;
+    auto key = [&](int k) { return direction == TSP_FP ? chunks[k].v0 : chunks[k].z0; };
+    auto len = [&](int k) { return direction == TSP_FP ? chunks[k].v1 - chunks[k].v0 : chunks[k].z1 - chunks[k].z0; };
+    std::sort(sorted.begin(), sorted.end(), [&](int a, int b) { return key(a) < key(b); });
+    long long total = 0;
+    for (int k : sorted) total += len(k);
+    std::vector<std::vector<int>> share(n_devices);
+    long long acc = 0;
+    for (int k : sorted) {
+        const int d = (int)std::min<long long>(n_devices - 1, (acc + len(k) / 2) * n_devices / std::max(1LL, total));
+        share[d].push_back(k);
+        acc += len(k);
+    }
+    std::vector<int> rcs(n_devices, TSP_OK);
+    std::vector<std::string> errs(n_devices);
+    std::vector<std::thread> threads;
+    for (int d = 0; d < n_devices; ++d) {
+        threads.emplace_back([&, d]() {
+            if (share[d].empty()) return;
+            DeviceGuard guard;
+            if (guard.enter(devices[d]) != 0) { rcs[d] = TSP_ERR_CUDA; errs[d] = "cannot switch device"; return; }
+            cudaStream_t s = nullptr;
+            if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) != cudaSuccess) { rcs[d] = TSP_ERR_CUDA; errs[d] = "cannot create a stream"; return; }
+            rcs[d] = project_host_chunks(pr, devices[d], direction, (float *)vol, (float *)proj, share[d], s, host_mem_cap(), nullptr);
+            if (rcs[d]) errs[d] = g_last_error;  // thread-local message of the worker
+            cudaStreamDestroy(s);
+        });
+    }
+    for (auto &t : threads) t.join();
+    pr->host_pipelined = 1;
+    pr->host_devices = n_devices;
+    for (int d = 0; d < n_devices; ++d)
+        if (rcs[d]) return fail(rcs[d], "device %d: %s", devices[d], errs[d].c_str());
+    return TSP_OK;
 }
 
 extern "C" int tsp_project(tsp_projector *pr, int direction, int additive, void *vol, void *proj, int batch,
@@ -1196,11 +1391,14 @@ extern "C" int tsp_project(tsp_projector *pr, int direction, int additive, void 
     if (memory_kind == TSP_MEM_HOST && batch == 1 && !additive && (nvox + npix) * sizeof(float) >= pipeline_min &&
         !getenv("TSP_HOST_NO_PIPELINE") && plan_host_pipeline(pr)) {
         pr->host_pipelined = 1;
-        return project_host_pipelined(pr, st, device, direction, (float *)vol, (float *)proj, stream);
+        pr->host_devices = 1;
+        return project_host_pipelined(pr, device, direction, (float *)vol, (float *)proj, stream);
     }
+    PipeResources res;  // releases the staging buffers on every exit path
+    res.stream = stream;
     if (memory_kind == TSP_MEM_HOST) {
-        CUDA_TRY(cudaMallocAsync(&dvol, nvox * batch * sizeof(float), stream));
-        CUDA_TRY(cudaMallocAsync(&dproj, npix * batch * sizeof(float), stream));
+        CUDA_TRY(res.alloc(st, &dvol, nvox * batch));
+        CUDA_TRY(res.alloc(st, &dproj, npix * batch));
         // inputs, and the destination too when accumulating
         if (direction == TSP_FP || additive)
             CUDA_TRY(cudaMemcpyAsync(dvol, vol, nvox * batch * sizeof(float), cudaMemcpyHostToDevice, stream));
@@ -1210,15 +1408,11 @@ extern "C" int tsp_project(tsp_projector *pr, int direction, int additive, void 
     int rc = TSP_OK;
     if (direction == TSP_FP) rc = launch_fp(pr, st, dvol, dproj, additive, stream, nullptr, nullptr, batch);
     else rc = launch_bp(pr, st, dvol, dproj, additive, stream, nullptr, batch);
-    if (memory_kind == TSP_MEM_HOST) {
-        if (rc == TSP_OK) {
-            if (direction == TSP_FP)
-                CUDA_TRY(cudaMemcpyAsync(proj, dproj, npix * batch * sizeof(float), cudaMemcpyDeviceToHost, stream));
-            else
-                CUDA_TRY(cudaMemcpyAsync(vol, dvol, nvox * batch * sizeof(float), cudaMemcpyDeviceToHost, stream));
-        }
-        cudaFreeAsync(dvol, stream);
-        cudaFreeAsync(dproj, stream);
+    if (memory_kind == TSP_MEM_HOST && rc == TSP_OK) {
+        if (direction == TSP_FP)
+            CUDA_TRY(cudaMemcpyAsync(proj, dproj, npix * batch * sizeof(float), cudaMemcpyDeviceToHost, stream));
+        else
+            CUDA_TRY(cudaMemcpyAsync(vol, dvol, nvox * batch * sizeof(float), cudaMemcpyDeviceToHost, stream));
         CUDA_TRY(cudaStreamSynchronize(stream));
     }
     return rc;
