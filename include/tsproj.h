@@ -179,6 +179,20 @@ int tsp_sirt(tsp_projector *projector, void *x, const void *y, const void *R, co
 int tsp_project_fused(tsp_projector *projector, int direction, void *vol, void *proj, const void *sub,
                       const void *mul, int device, void *cuda_stream);
 
+/*
+ * The element-wise passes of FDK around the ramp filter's FFT, replacing the filtering half of
+ * astra.experimental.accumulate_FDK (tomosipo/astra.py:404-406); the backprojection half is tsp_project(TSP_BP).
+ * Device arrays, asynchronous on the stream.  All rows are [det_rows][n_angles][pitch]:
+ *   stage 0  out[..][0 .. pitch) = proj * cosine weight * redundancy, zero beyond det_cols (the FFT's zero padding);
+ *            in = projections [det_rows][n_angles][det_cols]; redundancy: device float [n_angles][det_cols]
+ *            (Parker weights of a short scan) or NULL = 1/2 (full circle)
+ *   stage 1  out (float2 spectrum, pitch = aux / 2 + 1 bins of an aux-point real FFT) *= band-limited ramp; in unused
+ *   stage 2  out [det_rows][n_angles][det_cols] = in[..][0 .. det_cols) * per-angle constant; angle_weights: host
+ *            doubles [n_angles], the angular step d_beta per angle in radians, or NULL = 2 pi / n_angles
+ */
+int tsp_fdk_stage(tsp_projector *projector, int stage, const void *in, void *out, int pitch, int aux,
+                  const void *redundancy, const double *angle_weights, int device, void *cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

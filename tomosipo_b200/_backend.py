@@ -77,6 +77,7 @@ EXPORTED_SYMBOLS = (
     "tsp_projector_host_plan",
     "tsp_projector_bp_map",
     "tsp_project_multi",
+    "tsp_fdk_stage",
 )
 
 
@@ -132,6 +133,9 @@ def lib():
         L.tsp_projector_host_plan.restype = ctypes.c_int
         L.tsp_project_multi.argtypes = [vp, ctypes.c_int, ctypes.c_int, vp, vp, ctypes.POINTER(ctypes.c_int), ctypes.c_int]
         L.tsp_project_multi.restype = ctypes.c_int
+        L.tsp_fdk_stage.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_int, vp,
+                                    ctypes.POINTER(ctypes.c_double), ctypes.c_int, vp]
+        L.tsp_fdk_stage.restype = ctypes.c_int
         f64p = ctypes.POINTER(ctypes.c_double)
         L.tsp_projector_bp_map.argtypes = [vp, ctypes.c_int, f64p, f64p]
         L.tsp_projector_bp_map.restype = ctypes.c_int
@@ -209,6 +213,15 @@ class Projector:
         devs = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
         _check(lib().tsp_project_multi(self._handle, int(direction), int(bool(additive)), ctypes.c_void_p(vol_ptr),
                                        ctypes.c_void_p(proj_ptr), devs, len(devices)))
+
+    def fdk_stage(self, stage, in_ptr, out_ptr, pitch, aux, redundancy_ptr, angle_weights, device=0, stream=0):
+        """One element-wise pass of the FDK pre-filter on device pointers (``tsp_fdk_stage`` in include/tsproj.h)."""
+        vp = ctypes.c_void_p
+        aw = None
+        if angle_weights is not None:
+            aw = np.ascontiguousarray(angle_weights, dtype=np.float64).ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        _check(lib().tsp_fdk_stage(self._handle, int(stage), vp(in_ptr), vp(out_ptr), int(pitch), int(aux),
+                                   vp(redundancy_ptr), aw, int(device), vp(stream)))
 
     def sirt(self, x_ptr, y_ptr, r_ptr, c_ptr, ytmp_ptr, iterations, device=0, stream=0):
         vp = ctypes.c_void_p

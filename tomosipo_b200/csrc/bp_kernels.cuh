@@ -546,7 +546,14 @@ __global__ void __launch_bounds__(BP_THREADS) bp_kernel(const BPArgs P)
 constexpr int BP_TMA_PITCH = 68;
 constexpr int BP_TMA_PITCH_B = 60;  // alternative: consecutive rows start 4 banks *earlier*
 constexpr int BP_TMA_CONSUMERS = BP_TX * BP_TY;
-constexpr int BP_TMA_THREADS = BP_TMA_CONSUMERS + 32;
+// BP_PUBLISHER (experiment): a second helper warp waits on the TMA barriers and publishes "angles ready" in a plain
+// shared-memory word, which the consumers poll with ld.shared (29 cycles) instead of mbarrier.try_wait (90+).
+#ifdef BP_PUBLISHER
+constexpr int BP_TMA_HELPERS = 2;
+#else
+constexpr int BP_TMA_HELPERS = 1;
+#endif
+constexpr int BP_TMA_THREADS = BP_TMA_CONSUMERS + 32 * BP_TMA_HELPERS;
 #ifndef BP_TMA_STAGES_Z32
 #define BP_TMA_STAGES_Z32 4  // ring depth at 32 voxels per thread (tuning: -DBP_TMA_STAGES_Z32=n)
 #endif
@@ -556,7 +563,7 @@ __host__ __device__ constexpr size_t bp_tma_box_bytes(int zpt) { return (size_t)
 __host__ __device__ constexpr size_t bp_tma_stage_bytes(int zpt) { return (bp_tma_box_bytes(zpt) + 127) / 128 * 128; }
 __host__ __device__ constexpr size_t bp_tma_smem_bytes(int zpt)
 {
-    return bp_tma_stages(zpt) * (bp_tma_stage_bytes(zpt) + sizeof(BPLocal) + 16) + 128;
+    return bp_tma_stages(zpt) * (bp_tma_stage_bytes(zpt) + sizeof(BPLocal) + 16) + 128 + 16;
 }
 __host__ __device__ constexpr int bp_tma_min_ctas(int zpt) { return zpt >= 32 ? 2 : 3; }
 
@@ -620,6 +627,7 @@ bp_tma_kernel(const BPArgs P, const __grid_constant__ TensorMapPair tmaps)  // m
     const uint32_t bufs = smem_u32(base);
     const uint32_t full = smem_u32(loc + STAGES);
     const uint32_t empty = full + 8u * STAGES;
+    const uint32_t ready = empty + 8u * STAGES;  // BP_PUBLISHER: number of angles whose footprint has landed
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -635,10 +643,24 @@ bp_tma_kernel(const BPArgs P, const __grid_constant__ TensorMapPair tmaps)  // m
             mbar_init(full + 8u * s, 1);                       // the producer's arrive(+expect_tx)
             mbar_init(empty + 8u * s, BP_TMA_CONSUMERS / 32);  // one arrival per consumer warp
         }
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(ready), "r"(0u) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
+#ifdef BP_PUBLISHER
+    if (warp == BP_TMA_CONSUMERS / 32 + 1) {
+        // ----------------------------------------------------------- publisher
+        int s = 0;
+        uint32_t parity = 0u;
+        for (int angle = 0; angle < P.n_angles; ++angle) {
+            mbar_wait(full + 8u * s, parity);
+            if (lane == 0) asm volatile("st.volatile.shared.u32 [%0], %1;" ::"r"(ready), "r"((uint32_t)angle + 1u) : "memory");
+            if (++s == STAGES) { s = 0; parity ^= 1u; }
+        }
+        return;
+    }
+#endif
     if (warp == BP_TMA_CONSUMERS / 32) {
         // ------------------------------------------------------------ producer
         const int group = lane >> 3, corner = lane & 7;
@@ -689,7 +711,14 @@ bp_tma_kernel(const BPArgs P, const __grid_constant__ TensorMapPair tmaps)  // m
     int s = 0;
     uint32_t parity = 0u;
     for (int angle = 0; angle < P.n_angles; ++angle) {
-#ifndef BP_EXP_NOWAIT
+#ifdef BP_PUBLISHER
+        {
+            uint32_t r;
+            do {
+                asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(r) : "r"(ready) : "memory");
+            } while (r <= (uint32_t)angle);
+        }
+#else
         mbar_wait(full + 8u * s, parity);
 #endif
         if (in_xy)

@@ -39,7 +39,13 @@ struct FPTmaArgs {
     // (scratch/bank_sim_fp2.py).  The producer picks the variant per CTA; tmap[v] has box_w[v].
     int box_w[2];           // elements, multiples of 4
     int box_h;
-    uint32_t magic_off[2];  // -4 * MAGIC_BITS * (box_w + 1) mod 2^32 (run-time on purpose, see BPArgs)
+    // SPS consecutive slices share one ring stage (one barrier round trip, one control word, one TMA issue per
+    // stage: the hand-off is ~26 % of the instructions of a one-slice stage).  The staged box is then
+    // (box_w, SPS, box_h) or (box_w, box_h, SPS) elements and serves the footprints of all its slices.
+    int sps;                // 1 or 2
+    uint32_t row_stride4[2];  // bytes between consecutive q rows of a staged slice
+    uint32_t slice_off4[2];   // bytes between the slices of a stage
+    uint32_t magic_off[2];  // -4 * MAGIC_BITS * (row stride in words + 1) mod 2^32 (run-time on purpose, see BPArgs)
     int march_is_middle;    // tensor coordinates are (p, k, q) if set, (p, q, k) otherwise
     int stages;
     uint32_t stage_bytes;   // max box bytes rounded up to 128
@@ -113,11 +119,12 @@ __device__ __forceinline__ void fpt_consume(const FPTmaArgs &A, int kA, int kD, 
     // the column's shared p line
     const FPArgs &P = A.a;
     const float MAGIC = 12582912.0f;
-    const uint32_t bw4 = (uint32_t)A.box_w[V] * 4u;
+    const uint32_t rs4 = A.row_stride4[V], so4 = A.slice_off4[V];
+    const int sps = A.sps;
     float t = (float)kA + t0;
     int s = 0;
     uint32_t parity = 0u;
-    for (int k = kA; k < kD; ++k) {
+    for (int k = kA; k < kD; k += sps) {
         mbar_wait(full + 8u * s, parity);
         uint32_t sb, fit;
         asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(sb), "=r"(fit) : "r"(ctrl + 8u * s) : "memory");
@@ -125,53 +132,59 @@ __device__ __forceinline__ void fpt_consume(const FPTmaArgs &A, int kA, int kD, 
             // Two detector rows per step with Blackwell's packed fp32x2 arithmetic (FFMA2 / FADD2: two
             // independent fp32 operations per issue slot - the kernel is issue-bound): 10.5 instead
             // of 16 instructions per sample.  Every pair (.x, .y) = (row r, row r + 1).
-            const float2 M2 = make_float2(MAGIC, MAGIC), NEG1 = make_float2(-1.0f, -1.0f), t2 = make_float2(t, t);
-            float2 wp2 = make_float2(0.0f, 0.0f);
-            uint32_t offp0 = 0u, offp1 = 0u;
-            if (COLS) {
-                const float fp = fmaf(ap2[0].x, t, cp2[0].x);
-                const float rp = __fadd_rd(fp, MAGIC);
-                const float wp = fp - (rp - MAGIC);
-                wp2 = make_float2(wp, wp);
-                offp0 = offp1 = __float_as_uint(rp) * 4u + sb;
-            }
-#pragma unroll
-            for (int h = 0; h < R / 2; ++h) {
-                if (!COLS) {
-                    const float2 fp2 = __ffma2_rn(ap2[COLS ? 0 : h], t2, cp2[COLS ? 0 : h]);
-                    const float2 rp2 = __fadd2_rd(fp2, M2);
-                    wp2 = __fadd2_rn(fp2, __ffma2_rn(rp2, NEG1, M2));
-                    offp0 = __float_as_uint(rp2.x) * 4u + sb;
-                    offp1 = __float_as_uint(rp2.y) * 4u + sb;
+            const float2 M2 = make_float2(MAGIC, MAGIC), NEG1 = make_float2(-1.0f, -1.0f);
+            for (int j = 0; j < sps; ++j) {  // a slice past the hull's end samples zeros (its box is staged all the same)
+                const float tj = t + (float)j;
+                const float2 t2 = make_float2(tj, tj);
+                float2 wp2 = make_float2(0.0f, 0.0f);
+                uint32_t offp0 = 0u, offp1 = 0u;
+                if (COLS) {
+                    const float fp = fmaf(ap2[0].x, tj, cp2[0].x);
+                    const float rp = __fadd_rd(fp, MAGIC);
+                    const float wp = fp - (rp - MAGIC);
+                    wp2 = make_float2(wp, wp);
+                    offp0 = offp1 = __float_as_uint(rp) * 4u + sb;
                 }
-                const float2 fq2 = __ffma2_rn(aq2[h], t2, cq2[h]);
-                const float2 rq2 = __fadd2_rd(fq2, M2);                          // round-down add == floor
-                const float2 wq2 = __fadd2_rn(fq2, __ffma2_rn(rq2, NEG1, M2));  // fq - (rq - M)
-                const uint32_t a0 = __float_as_uint(rq2.x) * bw4 + offp0;
-                const uint32_t b0 = __float_as_uint(rq2.y) * bw4 + offp1;
-                const uint32_t a1 = a0 + bw4, b1 = b0 + bw4;
-                const float2 v00 = make_float2(fpt_lds<0>(a0), fpt_lds<0>(b0));
-                const float2 v10 = make_float2(fpt_lds<4>(a0), fpt_lds<4>(b0));
-                const float2 v01 = make_float2(fpt_lds<0>(a1), fpt_lds<0>(b1));
-                const float2 v11 = make_float2(fpt_lds<4>(a1), fpt_lds<4>(b1));
-                const float2 lo = __ffma2_rn(wp2, __ffma2_rn(v00, NEG1, v10), v00);
-                const float2 hi = __ffma2_rn(wp2, __ffma2_rn(v01, NEG1, v11), v01);
-                const float2 val = __ffma2_rn(wq2, __ffma2_rn(lo, NEG1, hi), lo);
-                acc2[h] = __fadd2_rn(acc2[h], val);
+#pragma unroll
+                for (int h = 0; h < R / 2; ++h) {
+                    if (!COLS) {
+                        const float2 fp2 = __ffma2_rn(ap2[COLS ? 0 : h], t2, cp2[COLS ? 0 : h]);
+                        const float2 rp2 = __fadd2_rd(fp2, M2);
+                        wp2 = __fadd2_rn(fp2, __ffma2_rn(rp2, NEG1, M2));
+                        offp0 = __float_as_uint(rp2.x) * 4u + sb;
+                        offp1 = __float_as_uint(rp2.y) * 4u + sb;
+                    }
+                    const float2 fq2 = __ffma2_rn(aq2[h], t2, cq2[h]);
+                    const float2 rq2 = __fadd2_rd(fq2, M2);                          // round-down add == floor
+                    const float2 wq2 = __fadd2_rn(fq2, __ffma2_rn(rq2, NEG1, M2));  // fq - (rq - M)
+                    const uint32_t a0 = __float_as_uint(rq2.x) * rs4 + offp0;
+                    const uint32_t b0 = __float_as_uint(rq2.y) * rs4 + offp1;
+                    const uint32_t a1 = a0 + rs4, b1 = b0 + rs4;
+                    const float2 v00 = make_float2(fpt_lds<0>(a0), fpt_lds<0>(b0));
+                    const float2 v10 = make_float2(fpt_lds<4>(a0), fpt_lds<4>(b0));
+                    const float2 v01 = make_float2(fpt_lds<0>(a1), fpt_lds<0>(b1));
+                    const float2 v11 = make_float2(fpt_lds<4>(a1), fpt_lds<4>(b1));
+                    const float2 lo = __ffma2_rn(wp2, __ffma2_rn(v00, NEG1, v10), v00);
+                    const float2 hi = __ffma2_rn(wp2, __ffma2_rn(v01, NEG1, v11), v01);
+                    const float2 val = __ffma2_rn(wq2, __ffma2_rn(lo, NEG1, hi), lo);
+                    acc2[h] = __fadd2_rn(acc2[h], val);
+                }
+                sb += so4;
             }
         } else {
+            const int k_end = min(k + sps, P.n_m);
 #pragma unroll
             for (int h = 0; h < R / 2; ++h) {
                 careful_range(P, COLS ? ap2[0].x : ap2[COLS ? 0 : h].x, aq2[h].x, COLS ? cp2[0].x : cp2[COLS ? 0 : h].x,
-                              cq2[h].x, t0, k, k + 1, acc2[h].x);
+                              cq2[h].x, t0, k, k_end, acc2[h].x);
                 careful_range(P, COLS ? ap2[0].x : ap2[COLS ? 0 : h].y, aq2[h].y, COLS ? cp2[0].x : cp2[COLS ? 0 : h].y,
-                              cq2[h].y, t0, k, k + 1, acc2[h].y);
+                              cq2[h].y, t0, k, k_end, acc2[h].y);
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + 8u * s);
         if (++s == A.stages) { s = 0; parity ^= 1u; }
-        t += 1.0f;
+        t += (float)sps;
     }
 }
 
@@ -256,13 +269,21 @@ fp_tma_kernel(const FPTmaArgs A, const __grid_constant__ TensorMapPair tmaps)
         int s = 0;
         uint32_t parity = 1u;
         const int bw = A.box_w[variant];
+        const int sps = A.sps;
+        const int rs = (int)(A.row_stride4[variant] >> 2);  // words between q rows of a staged slice
         const uint32_t moff = A.magic_off[variant];
-        const uint32_t box_bytes = (uint32_t)bw * (uint32_t)A.box_h * 4u;
+        const uint32_t box_bytes = (uint32_t)bw * (uint32_t)A.box_h * 4u * (uint32_t)sps;
         const TensorMapBlob *tm = tmap + variant;
-        for (int k0 = kA; k0 < kD; k0 += 32) {
-            const int k = k0 + lane;
+        for (int k0 = kA; k0 < kD; k0 += 32 * sps) {
+            const int k = k0 + lane * sps;  // this lane bounds the stage that starts at slice k
             float pmin, pmax, qmin, qmax;
             fpt_slice_box(c, (float)k + t0, pmin, pmax, qmin, qmax);
+            if (sps == 2) {  // union with the footprint on slice k + 1
+                float pmin1, pmax1, qmin1, qmax1;
+                fpt_slice_box(c, (float)(k + 1) + t0, pmin1, pmax1, qmin1, qmax1);
+                pmin = fminf(pmin, pmin1); pmax = fmaxf(pmax, pmax1);
+                qmin = fminf(qmin, qmin1); qmax = fmaxf(qmax, qmax1);
+            }
             // clamp far-away boxes so that the float -> int conversions are safe
             pmin = fmaxf(pmin, -1.0e6f); qmin = fmaxf(qmin, -1.0e6f);
             pmax = fminf(pmax, 1.0e6f); qmax = fminf(qmax, 1.0e6f);
@@ -271,7 +292,7 @@ fp_tma_kernel(const FPTmaArgs A, const __grid_constant__ TensorMapPair tmaps)
             const int q0 = __float2int_rd(qmin);
             const int fit = (__float2int_rd(pmax) + 2 - p0 <= bw) && (__float2int_rd(qmax) + 2 - q0 <= A.box_h) &&
                             (pmax >= pmin) && (qmax >= qmin);
-            const int nj = min(32, kD - k0);
+            const int nj = min(32, (kD - k0 + sps - 1) / sps);
             for (int j = 0; j < nj; ++j) {
                 const int p0j = __shfl_sync(0xffffffffu, p0, j);
                 const int q0j = __shfl_sync(0xffffffffu, q0, j);
@@ -279,13 +300,13 @@ fp_tma_kernel(const FPTmaArgs A, const __grid_constant__ TensorMapPair tmaps)
                 mbar_wait(empty + 8u * s, parity);
                 if (lane == 0) {
                     const uint32_t dst = bufs + (uint32_t)s * A.stage_bytes;
-                    const uint32_t sb = dst - 4u * (uint32_t)(q0j * bw + p0j) + moff;
+                    const uint32_t sb = dst - 4u * (uint32_t)(q0j * rs + p0j) + moff;
                     asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(ctrl + 8u * s), "r"(sb), "r"((uint32_t)fitj)
                                  : "memory");
                     if (fitj) {
                         mbar_arrive_expect_tx(full + 8u * s, box_bytes);
-                        if (A.march_is_middle) fpt_tma_box(dst, tm, p0j, k0 + j, q0j, full + 8u * s);
-                        else fpt_tma_box(dst, tm, p0j, q0j, k0 + j, full + 8u * s);
+                        if (A.march_is_middle) fpt_tma_box(dst, tm, p0j, k0 + j * sps, q0j, full + 8u * s);
+                        else fpt_tma_box(dst, tm, p0j, q0j, k0 + j * sps, full + 8u * s);
                     } else {
                         mbar_arrive(full + 8u * s);
                     }

@@ -41,6 +41,11 @@ __device__ __forceinline__ void thin_hat_weights(float f, int c, float &w0, floa
     w1 = fmaxf(0.0f, 1.0f - fabsf(x - 1.0f));
 }
 
+// A tap whose weight is exactly 0 (shifted window at a border, lanes outside their own slice interval) must not
+// contribute whatever it holds: 0 * Inf and 0 * NaN are NaN, while ASTRA's border mode and the tiled kernels read 0
+// there.  The load is predicated on the weight (one compare per weight, shared by the BT batch items).
+__device__ __forceinline__ float thin_tap(const float *s, float w) { return w != 0.0f ? __ldg(s) : 0.0f; }
+
 // grid: (det_u tiles of 32, angle tiles of 8, batch groups * det_v)
 template <bool CONE, int BT>
 __global__ void __launch_bounds__(32 * THIN_FP_ANGLES) fp_thin_kernel(const FPArgs P, int n_list, int batch,
@@ -107,14 +112,14 @@ __global__ void __launch_bounds__(32 * THIN_FP_ANGLES) fp_thin_kernel(const FPAr
 #pragma unroll
         for (int j = 0; j < BT; ++j) {
             const float *s = vol0 + (ob[j] + off);
-            acc[j] = fmaf(w00, __ldg(s), fmaf(w01, __ldg(s + 1), acc[j]));
+            acc[j] = fmaf(w00, thin_tap(s, w00), fmaf(w01, thin_tap(s + 1, w01), acc[j]));
         }
         if (wq1 != 0.0f) {
             const float w10 = wq1 * wp0, w11 = wq1 * wp1;
 #pragma unroll
             for (int j = 0; j < BT; ++j) {
                 const float *s = vol0 + (ob[j] + off + sq32);
-                acc[j] = fmaf(w10, __ldg(s), fmaf(w11, __ldg(s + 1), acc[j]));
+                acc[j] = fmaf(w10, thin_tap(s, w10), fmaf(w11, thin_tap(s + 1, w11), acc[j]));
             }
         }
     }
@@ -223,14 +228,14 @@ __global__ void __launch_bounds__(BP_THREADS) bp_thin_kernel(const BPArgs P, int
 #pragma unroll
                     for (int b = 0; b < BT; ++b) {
                         const float *s = proj0 + (ob[b] + off);
-                        acc[i][b] = fmaf(w00, __ldg(s), fmaf(w01, __ldg(s + 1), acc[i][b]));
+                        acc[i][b] = fmaf(w00, thin_tap(s, w00), fmaf(w01, thin_tap(s + 1, w01), acc[i][b]));
                     }
                     if (wv1 != 0.0f) {
                         const float w10 = wv1 * wu0, w11 = wv1 * wu1;
 #pragma unroll
                         for (int b = 0; b < BT; ++b) {
                             const float *s = proj0 + (ob[b] + off + rp32);
-                            acc[i][b] = fmaf(w10, __ldg(s), fmaf(w11, __ldg(s + 1), acc[i][b]));
+                            acc[i][b] = fmaf(w10, thin_tap(s, w10), fmaf(w11, thin_tap(s + 1, w11), acc[i][b]));
                         }
                     }
                     nu += L[2]; nv += L[6];

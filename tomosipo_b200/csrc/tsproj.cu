@@ -18,6 +18,7 @@
 
 #include "bp_kernels.cuh"
 #include "fp_kernels.cuh"
+#include "fdk_kernels.cuh"
 #include "fp_tma_kernels.cuh"
 #include "thin_kernels.cuh"
 #include "tsp_internal.h"
@@ -595,45 +596,59 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
             const bool middle = grp.march != 2;                // marching along the middle layout axis?
             const uint64_t dims[3] = {(uint64_t)P.n_p, (uint64_t)n_second, (uint64_t)g.nz};
             const uint64_t strides[2] = {(uint64_t)pitch_p * 4, (uint64_t)pitch_p * 4 * (uint64_t)n_second};
-            // two pitch variants: box widths >= the needed width whose residue mod 32 banks is
-            // {4, 8} (column and row move together along a warp) or {24, 28} (opposite)
+            // slices per ring stage: 2 halves the per-slice hand-off (TSP_FP_SPS=1: one slice per stage)
+            int sps = 2;
+            if (const char *e = getenv("TSP_FP_SPS")) sps = atoi(e) == 1 ? 1 : 2;
+            if (P.n_m < 2) sps = 1;
+            // keep at least three ring stages in the shared-memory budget of the launch
+            if ((size_t)(grp.box_w + 36) * (grp.box_h + 1) * 2 * 4 * 3 > (size_t)(grp.rows_per_thread == 8 ? 108 : 72) * 1024) sps = 1;
+            // the footprint moves by at most one voxel per slice in p and in q (the marching axis dominates the ray)
+            const int need_w = (grp.box_w + (sps - 1) + 3) / 4 * 4, box_h = grp.box_h + (sps - 1);
+            // two pitch variants: box widths >= the needed width for which the row stride of a staged slice
+            // (box width x slices per stage when the marching axis is the middle tensor dimension) has a residue
+            // mod 32 banks of {4, 8} (column and row move together along a warp) or {24, 28} (opposite)
+            const int mult = middle ? sps : 1;
             int bw[2] = {0, 0};
-            for (int w = grp.box_w; w <= grp.box_w + 32 && !(bw[0] && bw[1]); w += 4) {
-                const int r = w & 31;
+            for (int w = need_w; w <= need_w + 32 && !(bw[0] && bw[1]); w += 4) {
+                const int r = (w * mult) & 31;
                 if (!bw[0] && (r == 4 || r == 8)) bw[0] = w;
                 if (!bw[1] && (r == 24 || r == 28)) bw[1] = w;
             }
-            if (getenv("TSP_FP_ONE_PITCH")) bw[0] = bw[1] = grp.box_w;
+            if (getenv("TSP_FP_ONE_PITCH")) bw[0] = bw[1] = need_w;
             // (the wider box costs L2 -> shared traffic, which has headroom: 26 % of the crossbar peak
             // at cfg 3, while the shared-memory pipe is the busiest unit of this kernel)
-            if (!bw[0]) bw[0] = bw[1] ? bw[1] : grp.box_w;
+            if (!bw[0]) bw[0] = bw[1] ? bw[1] : need_w;
             if (!bw[1]) bw[1] = bw[0];
-            if (bw[0] > 256 || bw[1] > 256) bw[0] = bw[1] = grp.box_w;
+            if (bw[0] > 256 || bw[1] > 256) bw[0] = bw[1] = need_w;
             TensorMapPair slot;
-            bool ok = true;
+            bool ok = box_h <= 256;
             for (int v = 0; v < 2 && ok; ++v) {
-                const uint32_t box[3] = {(uint32_t)bw[v], middle ? 1u : (uint32_t)grp.box_h, middle ? (uint32_t)grp.box_h : 1u};
+                const uint32_t box[3] = {(uint32_t)bw[v], middle ? (uint32_t)sps : (uint32_t)box_h, middle ? (uint32_t)box_h : (uint32_t)sps};
                 ok = make_tensor_map_3d(P.vol, dims, strides, box, &slot.m[v]);
             }
             if (ok) {
                 FPTmaArgs T;
                 T.a = P;
                 T.pairs = st->fp_pairs + 2 * st->pair_offset[gi];
-                T.box_h = grp.box_h;
+                T.box_h = box_h;
+                T.sps = sps;
                 for (int v = 0; v < 2; ++v) {
                     T.box_w[v] = bw[v];
-                    T.magic_off[v] = 0u - 4u * 0x4B400000u * (uint32_t)(bw[v] + 1);
+                    const uint32_t rs = (uint32_t)bw[v] * (middle ? (uint32_t)sps : 1u);  // words between q rows of one slice
+                    T.row_stride4[v] = 4u * rs;
+                    T.slice_off4[v] = 4u * (middle ? (uint32_t)bw[v] : (uint32_t)bw[v] * (uint32_t)box_h);
+                    T.magic_off[v] = 0u - 4u * 0x4B400000u * (rs + 1u);
                 }
                 T.march_is_middle = middle ? 1 : 0;
-                T.stage_bytes = ((uint32_t)std::max(bw[0], bw[1]) * grp.box_h * 4u + 127u) / 128u * 128u;
+                T.stage_bytes = ((uint32_t)std::max(bw[0], bw[1]) * box_h * sps * 4u + 127u) / 128u * 128u;
                 const int R = grp.rows_per_thread;
                 int stages = (int)(((R == 8 ? 108u : 72u) * 1024u) / (T.stage_bytes + 24u));
                 if (const char *e = getenv("TSP_FP_STAGES")) stages = atoi(e);
                 T.stages = std::max(2, std::min(stages, 12));
                 if (getenv("TSP_DEBUG"))
-                    fprintf(stderr, "[tsp] fp group march=%d transposed=%d cols=%d R=%d: %zu pairs, box need %dx%d, pitches %d/%d, %d stages of %u B\n",
+                    fprintf(stderr, "[tsp] fp group march=%d transposed=%d cols=%d R=%d: %zu pairs, box need %dx%d, pitches %d/%d, %d slices per stage, %d stages of %u B\n",
                             grp.march, (int)grp.transposed, (int)grp.columns, R, grp.pairs.size() / 2, grp.box_w, grp.box_h,
-                            bw[0], bw[1], T.stages, T.stage_bytes);
+                            bw[0], bw[1], sps, T.stages, T.stage_bytes);
                 const size_t smem = 128 + (size_t)T.stages * (T.stage_bytes + 24) + 16;
                 dim3 tgrid((g.det_cols + FPT_TU - 1) / FPT_TU, (unsigned)(grp.pairs.size() / 2),
                            (g.det_rows + 4 * R - 1) / (4 * R));
@@ -1469,4 +1484,108 @@ extern "C" int tsp_project_fused(tsp_projector *pr, int direction, void *vol, vo
     if (direction == TSP_FP)
         return launch_fp(pr, st, (const float *)vol, (float *)proj, 0, stream, (const float *)sub, (const float *)mul);
     return launch_bp(pr, st, (float *)vol, (const float *)proj, 0, stream, (const float *)mul);
+}
+
+// -------------------------------------------------------------------- FDK --
+// Per-angle constants of a circular cone-beam scan, recovered from the vectors (fp64): pitches, source - detector-plane
+// distance, principal point, and the constant that turns the library's backprojection of the filtered rows into
+//   f = integral d_beta * redundancy * SOD^2 / (SOD - depth)^2 * q :
+// the backprojector applies V_vox * SDD^2 / (|u||v| (SOD - depth)^2), the filter is defined at the isocentre pitch
+// tau = |u| SOD / SDD, hence  scale = d_beta * SOD^2 |u||v| / (SDD^2 V_vox tau).  (The redundancy weight - 1/2 for a
+// full circle, Parker's for a short scan - is applied before the filter by fdk_preweight_kernel.)
+static int fdk_angle_constants(const tsp_projector *pr, const double *angle_weights, std::vector<FDKAngle> &tab)
+{
+    const tsp_geometry &g = pr->g;
+    if (g.kind != TSP_KIND_CONE_VEC) return fail(TSP_ERR_INVALID, "FDK needs a cone-beam projection geometry");
+    const double vox = pr->sigma[0] * pr->sigma[1] * pr->sigma[2];
+    tab.resize(g.n_angles);
+    for (int a = 0; a < g.n_angles; ++a) {
+        const double *w = pr->vectors.data() + 12 * (size_t)a;
+        const double *src = w, *det = w + 3, *u = w + 6, *v = w + 9;
+        const double pu = std::sqrt(u[0] * u[0] + u[1] * u[1] + u[2] * u[2]);
+        const double pv = std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+        double n[3] = {u[1] * v[2] - u[2] * v[1], u[2] * v[0] - u[0] * v[2], u[0] * v[1] - u[1] * v[0]};
+        const double nn = std::sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        if (!(nn > 0.0) || !(pu > 0.0) || !(pv > 0.0)) return fail(TSP_ERR_INVALID, "degenerate detector at angle %d", a);
+        double h = 0.0, hs = 0.0;
+        for (int i = 0; i < 3; ++i) {
+            n[i] /= nn;
+            h += (det[i] - src[i]) * n[i];
+            hs += (0.5 * (g.win_min[i] + g.win_max[i]) - src[i]) * n[i];
+        }
+        const double sdd = std::fabs(h), sod = std::fabs(hs);
+        double ppu = 0.0, ppv = 0.0;
+        for (int i = 0; i < 3; ++i) {
+            const double foot = src[i] + h * n[i] - det[i];
+            ppu += foot * u[i];
+            ppv += foot * v[i];
+        }
+        FDKAngle &t = tab[a];
+        t.pu = (float)pu; t.pv = (float)pv; t.sdd = (float)sdd;
+        t.ppu = (float)(ppu / (pu * pu)); t.ppv = (float)(ppv / (pv * pv));
+        const double dbeta = angle_weights ? angle_weights[a] : 2.0 * M_PI / g.n_angles;
+        const double tau = pu * sod / sdd;
+        t.scale = (float)(dbeta * sod * sod * pu * pv / (sdd * sdd * vox * tau));
+    }
+    return TSP_OK;
+}
+
+// stage: 0 = pre-weight + pad   (in: proj [V][A][U],            out: padded rows [V][A][pitch])
+//        1 = ramp multiply      (in/out: spectrum float2 [V][A][pitch], pitch = nfft / 2 + 1 bins; aux = nfft)
+//        2 = crop + scale       (in: filtered rows [V][A][pitch], out: q [V][A][U])
+extern "C" int tsp_fdk_stage(tsp_projector *pr, int stage, const void *in, void *out, int pitch, int aux,
+                             const void *redundancy, const double *angle_weights, int device, void *cuda_stream)
+{
+    if (!pr || !out || (stage != 1 && !in)) return fail(TSP_ERR_INVALID, "NULL argument");
+    if (stage < 0 || stage > 2) return fail(TSP_ERR_INVALID, "stage must be 0, 1 or 2");
+    const int ndev = tsp_device_count();
+    if (ndev == 0) return fail(TSP_ERR_CUDA, "no CUDA device available (libtsproj has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(TSP_ERR_INVALID, "device %d out of range [0, %d)", device, ndev);
+    const tsp_geometry &g = pr->g;
+    if (pitch < (stage == 1 ? 2 : g.det_cols)) return fail(TSP_ERR_INVALID, "pitch %d too small", pitch);
+    const long long rows = (long long)g.det_rows * g.n_angles;
+    if (rows > 2147483647LL) return fail(TSP_ERR_INVALID, "too many detector rows x angles for the FDK grid");
+    DeviceGuard guard;
+    if (guard.enter(device) != 0) return fail(TSP_ERR_CUDA, "cannot switch to device %d", device);
+    DeviceState *st = nullptr;
+    if (int rc = get_device_state(pr, device, &st)) return rc;
+    cudaStream_t stream = (cudaStream_t)cuda_stream;
+    PoolScratch tab_d;
+    tab_d.stream = stream;
+    if (stage != 1) {
+        std::vector<FDKAngle> tab;
+        if (int rc = fdk_angle_constants(pr, angle_weights, tab)) return rc;
+        CUDA_TRY(pool_alloc(st, &tab_d.p, tab.size() * sizeof(FDKAngle), stream));
+        // pageable source: the copy is staged by the runtime before the call returns, `tab` may go out of scope
+        CUDA_TRY(cudaMemcpyAsync(tab_d.p, tab.data(), tab.size() * sizeof(FDKAngle), cudaMemcpyHostToDevice, stream));
+    }
+    if (stage == 0) {
+        fdk_preweight_kernel<<<(unsigned)rows, 256, 0, stream>>>((const float *)in, (float *)out, (const FDKAngle *)tab_d.p,
+                                                                 (const float *)redundancy, g.det_cols, g.det_rows, g.n_angles, pitch);
+    } else if (stage == 1) {
+        // frequency response of the band-limited ramp h[0] = 1/4, h[n odd] = -1 / (pi n)^2 on an nfft-periodic grid
+        const int nfft = aux, nfreq = pitch;
+        if (nfft < 2 * g.det_cols || nfreq != nfft / 2 + 1) return fail(TSP_ERR_INVALID, "ramp: need nfft >= 2 U and nfft / 2 + 1 bins");
+        std::vector<float> G(nfreq);
+        for (int k = 0; k < nfreq; ++k) {
+            double acc = 0.25;
+            for (int n = 1; n <= nfft / 2; n += 2) {
+                const double hn = -1.0 / (M_PI * M_PI * (double)n * (double)n);
+                // n and nfft - n are both odd-indexed images of the same tap unless n == nfft / 2
+                acc += (2 * n == nfft ? 1.0 : 2.0) * hn * std::cos(2.0 * M_PI * (double)k * (double)n / (double)nfft);
+            }
+            G[k] = (float)acc;
+        }
+        PoolScratch G_d;
+        G_d.stream = stream;
+        CUDA_TRY(pool_alloc(st, &G_d.p, G.size() * sizeof(float), stream));
+        CUDA_TRY(cudaMemcpyAsync(G_d.p, G.data(), G.size() * sizeof(float), cudaMemcpyHostToDevice, stream));
+        fdk_ramp_kernel<<<(unsigned)rows, 256, 0, stream>>>((float2 *)out, (const float *)G_d.p, nfreq, (size_t)rows);
+    } else {
+        fdk_scale_crop_kernel<<<(unsigned)rows, 256, 0, stream>>>((const float *)in, (float *)out, (const FDKAngle *)tab_d.p,
+                                                                  g.det_cols, g.n_angles, pitch);
+    }
+    ++pr->launches;
+    CUDA_TRY(cudaGetLastError());
+    return TSP_OK;
 }
