@@ -24,6 +24,7 @@
 #ifndef TSPROJ_H
 #define TSPROJ_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -178,6 +179,15 @@ int tsp_sirt(tsp_projector *projector, void *x, const void *y, const void *R, co
  */
 int tsp_project_fused(tsp_projector *projector, int direction, void *vol, void *proj, const void *sub,
                       const void *mul, int device, void *cuda_stream);
+
+/*
+ * Page-locked host buffers for arrays the host-array path creates itself (the operator's outputs and the float32
+ * copies of float64 inputs; reference tomosipo/links/numpy.py:26-32,121-144 allocates them with numpy): transfers
+ * from / to pageable memory do not overlap the kernels.  Freed buffers are cached by size (TSP_PINNED_CACHE_MB,
+ * default 1024).  tsp_host_alloc returns NULL without a CUDA device - the caller then uses ordinary memory.
+ */
+void *tsp_host_alloc(size_t bytes);
+void tsp_host_free(void *buffer);
 
 /*
  * The element-wise passes of FDK around the ramp filter's FFT, replacing the filtering half of

@@ -361,3 +361,112 @@ def test_full_size_properties_1024():
     del y, x
     out = torch.zeros_like(bp)
     assert torch.equal(A.T(ones, out=out), bp)                 # deterministic
+
+
+def test_numpy_outputs_live_in_cached_pinned_buffers():
+    """Arrays the host path creates itself (operator outputs, float32 copies of float64 inputs) are page-locked
+    (tsp_host_alloc) so that their transfers overlap the kernels; a freed buffer is handed out again."""
+    import ctypes
+    import gc
+
+    from tomosipo_b200 import _backend as B
+
+    a = B.pinned_empty((256, 1024, 2))            # 2 MB: above the pinning threshold
+    assert a.dtype == np.float32 and a.flags.c_contiguous and a.flags.writeable
+    attr = ctypes.c_uint(0)
+    err = torch.cuda.cudart().cudaHostGetFlags(a.ctypes.data) if hasattr(torch.cuda.cudart(), "cudaHostGetFlags") else None
+    ptr = a.ctypes.data
+    a[...] = 3.0
+    del a
+    gc.collect()
+    b = B.pinned_empty((256, 1024, 2))
+    assert b.ctypes.data == ptr                   # served from the cache
+    assert B.pinned_empty((4, 4)).base is None    # small arrays stay ordinary numpy arrays
+    vg = ts.volume(shape=96, size=1)
+    pg = ts.cone(angles=48, shape=(96, 144), size=(1.875, 2.8125), src_orig_dist=4, src_det_dist=6)
+    A = ts.operator(vg, pg)
+    x64 = np.random.default_rng(0).random(A.domain_shape)              # float64, like the README loop
+    with pytest.warns(UserWarning):
+        y = A(x64)
+    assert y.dtype == np.float32 and y.base is not None                # pinned-backed output
+    assert rel_l2(y, oracle_of(A).fp(x64)) < TOL
+    del attr, err
+
+
+def test_cupy_link_on_real_device_memory(monkeypatch):
+    """CuPy itself is absent from the image (a11).  The link only touches a handful of cupy names, so a stand-in
+    module whose arrays live in REAL device memory (torch CUDA storage behind the cupy.ndarray surface) drives the
+    whole CupyLink -> RawBuffer -> C ABI -> kernel path: device pointer, device id, current stream, same-device
+    allocation of the output.  Also the cupy <-> torch compatibility the reference leaves as a TODO
+    (tomosipo/links/cupy.py:66-72): projecting a CuPy volume into a torch CUDA tensor."""
+    import importlib
+    import sys
+    import types
+
+    class _Dev:
+        def __init__(self, id_):
+            self.id = id_
+            self._ctx = None
+
+        def __enter__(self):
+            self._ctx = torch.cuda.device(self.id)
+            self._ctx.__enter__()
+            return self
+
+        def __exit__(self, *a):
+            return self._ctx.__exit__(*a)
+
+        def __eq__(self, other):
+            return isinstance(other, _Dev) and other.id == self.id
+
+    class FakeArray:
+        def __init__(self, t):
+            self.t = t
+
+        shape = property(lambda self: tuple(self.t.shape))
+        dtype = property(lambda self: {torch.float32: np.dtype("float32"), torch.float64: np.dtype("float64")}[self.t.dtype])
+        flags = property(lambda self: {"C_CONTIGUOUS": self.t.is_contiguous()})
+        data = property(lambda self: types.SimpleNamespace(ptr=self.t.data_ptr()))
+        device = property(lambda self: _Dev(self.t.device.index))
+
+        def astype(self, dt):
+            return FakeArray(self.t.to(torch.float32))
+
+        def copy(self):
+            return FakeArray(self.t.clone())
+
+    fake = types.ModuleType("cupy")
+    fake.ndarray = FakeArray
+    fake.float32 = np.dtype("float32")
+    mk = lambda f: (lambda shape, *a, dtype=None: FakeArray(f(tuple(shape), *a, dtype=torch.float32, device="cuda")))  # noqa: E731
+    fake.zeros, fake.empty = mk(torch.zeros), mk(torch.empty)
+    fake.full = lambda shape, value, dtype=None: FakeArray(torch.full(tuple(shape), float(value), device="cuda"))
+    fake.ascontiguousarray = lambda a: FakeArray(a.t.contiguous())
+    # CuPy keeps its own current stream (here: the default stream), whatever torch's current stream is
+    fake.cuda = types.SimpleNamespace(
+        get_current_stream=lambda: types.SimpleNamespace(ptr=torch.cuda.default_stream().cuda_stream))
+    monkeypatch.setitem(sys.modules, "cupy", fake)
+    sys.modules.pop("tomosipo_b200.links.cupy", None)
+    n_backends = len(ts.links.base.backends)
+    try:
+        importlib.import_module("tomosipo_b200.links.cupy")
+        vg = ts.volume(shape=(40, 48, 56), size=(0.8, 1, 1.1))
+        pg = ts.cone(angles=30, shape=(40, 72), size=(1.6, 2.9), src_orig_dist=4, src_det_dist=6)
+        A = ts.operator(vg, pg)
+        g = torch.Generator(device="cuda").manual_seed(3)
+        x = torch.rand(A.domain_shape, device="cuda", generator=g)
+        y_t = A(x)
+        y_c = A(FakeArray(x))                                   # CuPy in -> CuPy out, allocated by the link
+        assert isinstance(y_c, FakeArray) and torch.equal(y_c.t, y_t)
+        xb_c = A.T(y_c)
+        assert isinstance(xb_c, FakeArray) and torch.equal(xb_c.t, A.T(y_t))
+        out = torch.zeros_like(y_t)                             # CuPy volume -> torch projections (mixed links)
+        side = torch.cuda.Stream()
+        with torch.cuda.stream(side):                           # ... with the output bound to another stream
+            A(FakeArray(x), out=out)
+        side.synchronize()
+        assert torch.equal(out, y_t)
+        assert rel_l2(y_c.t.cpu().numpy(), oracle_of(A).fp(x.cpu().numpy().astype(np.float64))) < TOL
+    finally:
+        del ts.links.base.backends[n_backends:]
+        sys.modules.pop("tomosipo_b200.links.cupy", None)

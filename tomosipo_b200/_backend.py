@@ -78,6 +78,8 @@ EXPORTED_SYMBOLS = (
     "tsp_projector_bp_map",
     "tsp_project_multi",
     "tsp_fdk_stage",
+    "tsp_host_alloc",
+    "tsp_host_free",
 )
 
 
@@ -136,6 +138,10 @@ def lib():
         L.tsp_fdk_stage.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_int, vp,
                                     ctypes.POINTER(ctypes.c_double), ctypes.c_int, vp]
         L.tsp_fdk_stage.restype = ctypes.c_int
+        L.tsp_host_alloc.argtypes = [ctypes.c_size_t]
+        L.tsp_host_alloc.restype = vp
+        L.tsp_host_free.argtypes = [vp]
+        L.tsp_host_free.restype = None
         f64p = ctypes.POINTER(ctypes.c_double)
         L.tsp_projector_bp_map.argtypes = [vp, ctypes.c_int, f64p, f64p]
         L.tsp_projector_bp_map.restype = ctypes.c_int
@@ -152,6 +158,43 @@ def _check(rc):
     if rc == ERR_NOMEM:
         raise MemoryError(msg)
     raise RuntimeError(msg)
+
+
+class _PinnedOwner:
+    """Returns a page-locked buffer to the library's cache when the last array on it is gone."""
+
+    def __init__(self, ptr):
+        self.ptr = ptr
+
+    def __del__(self):
+        ptr, self.ptr = self.ptr, None
+        if ptr and _lib is not None:
+            try:
+                _lib.tsp_host_free(ctypes.c_void_p(ptr))
+            except Exception:  # interpreter shutdown
+                pass
+
+
+#: arrays smaller than this are not worth a page-locked buffer
+PINNED_MIN_BYTES = 1 << 20
+
+
+def pinned_empty(shape, dtype=np.float32):
+    """Uninitialised array in page-locked host memory (``tsp_host_alloc``), or an ordinary ``np.empty`` when the
+    array is small, pinning is switched off (``TSP_NO_PINNED=1``) or no CUDA device / library is available."""
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape, dtype=np.int64)) * dtype.itemsize
+    if nbytes < PINNED_MIN_BYTES or os.environ.get("TSP_NO_PINNED"):
+        return np.empty(shape, dtype=dtype)
+    try:
+        ptr = lib().tsp_host_alloc(nbytes)
+    except (ImportError, OSError):
+        ptr = None
+    if not ptr:
+        return np.empty(shape, dtype=dtype)
+    buf = (ctypes.c_byte * nbytes).from_address(ptr)
+    buf._owner = _PinnedOwner(ptr)  # np.frombuffer keeps `buf` (and with it the owner) alive as the array's base
+    return np.frombuffer(buf, dtype=dtype).reshape(shape)
 
 
 def cuda_available():

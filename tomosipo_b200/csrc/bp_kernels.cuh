@@ -93,33 +93,13 @@ __device__ __forceinline__ float bp_sample_global(const float *__restrict__ proj
     return fmaf(wv, hi - lo, lo);
 }
 
-// Eight threads per angle: each projects one corner of the tile's voxel-centre
-// box; shuffles reduce the bounding box; lane 0 writes the local map.
-__device__ __forceinline__ void bp_setup(const BPArgs &P, const BPAngle *__restrict__ ang, int corner,
-                                         double xc, double yc, double zc, double hx, double hy,
-                                         double hz, int max_rows, int max_cols, int alt_cols, int u_align, bool allow_rows3, int rows_loop, BPLocal *out)
+// Second half of the set-up, shared by both front ends: from the centre values (fp64) and the bounding box of the
+// tile's footprint to the tile-local map, the staged box and the loop the consumers take.
+__device__ __forceinline__ void bp_finish_setup(const BPArgs &P, const BPAngle *__restrict__ ang, double den_c, double nu_c,
+                                                double nv_c, double umin, double umax, double vmin, double vmax,
+                                                double dmin, double dmax, double hz, int max_rows, int max_cols,
+                                                int alt_cols, int u_align, bool allow_rows3, int rows_loop, BPLocal *out)
 {
-    const double den_c = ang->dn[0] * xc + ang->dn[1] * yc + ang->dn[2] * zc + ang->dn[3];
-    const double nu_c = ang->nu[0] * xc + ang->nu[1] * yc + ang->nu[2] * zc + ang->nu[3];
-    const double nv_c = ang->nv[0] * xc + ang->nv[1] * yc + ang->nv[2] * zc + ang->nv[3];
-    const double dx = (corner & 1) ? hx : -hx;
-    const double dy = (corner & 2) ? hy : -hy;
-    const double dz = (corner & 4) ? hz : -hz;
-    const double den = den_c + ang->dn[0] * dx + ang->dn[1] * dy + ang->dn[2] * dz;
-    const double uu = (nu_c + ang->nu[0] * dx + ang->nu[1] * dy + ang->nu[2] * dz) / den;
-    const double vv = (nv_c + ang->nv[0] * dx + ang->nv[1] * dy + ang->nv[2] * dz) / den;
-    double umin = uu, umax = uu, vmin = vv, vmax = vv, dmin = den, dmax = den;
-#pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {
-        umin = fmin(umin, __shfl_xor_sync(0xffffffffu, umin, o));
-        umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, o));
-        vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
-        vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-        dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
-        dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
-    }
-    if (corner != 0) return;
-
     BPLocal L;
     int mode = BP_SMEM;
     // The projective map is monotone over the box only if den keeps its sign.
@@ -161,13 +141,17 @@ __device__ __forceinline__ void bp_setup(const BPArgs &P, const BPAngle *__restr
             }
         }
     }
+    // (Folding the run's first dz into bu / bv / bd - 6 instead of 9 FMAs per thread and angle - and reading the map
+    // through an opaque base register without the S2R that ptxas re-issues per use were both measured SLOWER:
+    // 48.9 / 48.7 vs 48.0 ms in one run, r02 GPU call 9.  The unrolled loop's schedule is what matters.)
+    const double au2 = ang->nu[2] - off_u * ang->dn[2], av2 = ang->nv[2] - off_v * ang->dn[2];
     L.au[0] = (float)(ang->nu[0] - off_u * ang->dn[0]);
     L.au[1] = (float)(ang->nu[1] - off_u * ang->dn[1]);
-    L.au[2] = (float)(ang->nu[2] - off_u * ang->dn[2]);
+    L.au[2] = (float)au2;
     L.bu = (float)(nu_c - off_u * den_c);
     L.av[0] = (float)(ang->nv[0] - off_v * ang->dn[0]);
     L.av[1] = (float)(ang->nv[1] - off_v * ang->dn[1]);
-    L.av[2] = (float)(ang->nv[2] - off_v * ang->dn[2]);
+    L.av[2] = (float)av2;
     L.bv = (float)(nv_c - off_v * den_c);
     L.ad[0] = (float)ang->dn[0];
     L.ad[1] = (float)ang->dn[1];
@@ -178,12 +162,10 @@ __device__ __forceinline__ void bp_setup(const BPArgs &P, const BPAngle *__restr
     L.weight = (float)ang->weight;
     // U (and the cone magnification) independent of z over this tile?  Exact zeros for
     // detectors whose rows are parallel to the z axis (all circular geometries).
-    const double au2 = ang->nu[2] - off_u * ang->dn[2];
     L.z_invariant = ((fabs(au2) + 64.0 * fabs(ang->dn[2])) * (2.0 * hz + 1.0) < 1e-7 * fabs(den_c)) ? 1 : 0;
     if (L.z_invariant && mode != BP_GLOBAL && mode != BP_SKIP && allow_rows3) {
         // row step per voxel, dv = av2 / den, largest where |den| is smallest on the tile; the 3-row
         // loop also reads row j+2 of the last voxel pair: one spare row must fit the staged box
-        const double av2 = ang->nv[2] - off_v * ang->dn[2];
         const double dvmax = fabs(av2) / fmin(fabs(dmin), fabs(dmax));
         const bool positive = (av2 >= 0.0) == (den_c > 0.0);
         // (the row walk reads no spare row)
@@ -191,6 +173,74 @@ __device__ __forceinline__ void bp_setup(const BPArgs &P, const BPAngle *__restr
     }
     L.pad = 0;
     *out = L;
+}
+
+// Eight threads per angle: each projects one corner of the tile's voxel-centre
+// box; shuffles reduce the bounding box; lane 0 writes the local map.
+__device__ __forceinline__ void bp_setup(const BPArgs &P, const BPAngle *__restrict__ ang, int corner,
+                                         double xc, double yc, double zc, double hx, double hy,
+                                         double hz, int max_rows, int max_cols, int alt_cols, int u_align, bool allow_rows3, int rows_loop, BPLocal *out)
+{
+    const double den_c = ang->dn[0] * xc + ang->dn[1] * yc + ang->dn[2] * zc + ang->dn[3];
+    const double nu_c = ang->nu[0] * xc + ang->nu[1] * yc + ang->nu[2] * zc + ang->nu[3];
+    const double nv_c = ang->nv[0] * xc + ang->nv[1] * yc + ang->nv[2] * zc + ang->nv[3];
+    const double dx = (corner & 1) ? hx : -hx;
+    const double dy = (corner & 2) ? hy : -hy;
+    const double dz = (corner & 4) ? hz : -hz;
+    const double den = den_c + ang->dn[0] * dx + ang->dn[1] * dy + ang->dn[2] * dz;
+    const double uu = (nu_c + ang->nu[0] * dx + ang->nu[1] * dy + ang->nu[2] * dz) / den;
+    const double vv = (nv_c + ang->nv[0] * dx + ang->nv[1] * dy + ang->nv[2] * dz) / den;
+    double umin = uu, umax = uu, vmin = vv, vmax = vv, dmin = den, dmax = den;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+        umin = fmin(umin, __shfl_xor_sync(0xffffffffu, umin, o));
+        umax = fmax(umax, __shfl_xor_sync(0xffffffffu, umax, o));
+        vmin = fmin(vmin, __shfl_xor_sync(0xffffffffu, vmin, o));
+        vmax = fmax(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+        dmin = fmin(dmin, __shfl_xor_sync(0xffffffffu, dmin, o));
+        dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    }
+    if (corner != 0) return;
+    bp_finish_setup(P, ang, den_c, nu_c, nv_c, umin, umax, vmin, vmax, dmin, dmax, hz, max_rows, max_cols, alt_cols, u_align,
+                    allow_rows3, rows_loop, out);
+}
+
+// One lane = one angle (the TMA kernel's producer: 32 angles per pass).  The centre values and everything that enters
+// the fractional weights stay fp64; the footprint's bounding box - which only has to be right to a fraction of the
+// one-pixel margin the staged box carries - comes from the 8 corners in fp32, widened by 1/128 pixel.  No shuffles,
+// no fp64 divisions: ~6 producer instructions per (tile, angle) instead of ~100 for the 8-lanes-per-angle front end
+// (measured: the producer's set-up cost 7 % of the kernel, r02 GPU call 4).
+__device__ __forceinline__ void bp_setup_lane(const BPArgs &P, const BPAngle *__restrict__ ang, double xc, double yc,
+                                              double zc, float hx, float hy, float hz, int max_rows, int max_cols,
+                                              int alt_cols, int u_align, bool allow_rows3, int rows_loop, BPLocal *out)
+{
+    const double den_c = ang->dn[0] * xc + ang->dn[1] * yc + ang->dn[2] * zc + ang->dn[3];
+    const double nu_c = ang->nu[0] * xc + ang->nu[1] * yc + ang->nu[2] * zc + ang->nu[3];
+    const double nv_c = ang->nv[0] * xc + ang->nv[1] * yc + ang->nv[2] * zc + ang->nv[3];
+    const float dc = (float)den_c, uc = (float)nu_c, vc = (float)nv_c;
+    const float ddx = hx * (float)ang->dn[0], ddy = hy * (float)ang->dn[1], ddz = hz * (float)ang->dn[2];
+    const float dux = hx * (float)ang->nu[0], duy = hy * (float)ang->nu[1], duz = hz * (float)ang->nu[2];
+    const float dvx = hx * (float)ang->nv[0], dvy = hy * (float)ang->nv[1], dvz = hz * (float)ang->nv[2];
+    float umin = 3.0e38f, umax = -3.0e38f, vmin = 3.0e38f, vmax = -3.0e38f, dmin = 3.0e38f, dmax = -3.0e38f;
+    bool finite = true;
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float sx = (c & 1) ? 1.0f : -1.0f, sy = (c & 2) ? 1.0f : -1.0f, sz = (c & 4) ? 1.0f : -1.0f;
+        const float den = dc + sx * ddx + sy * ddy + sz * ddz;
+        const float r = 1.0f / den;
+        const float uu = (uc + sx * dux + sy * duy + sz * duz) * r;
+        const float vv = (vc + sx * dvx + sy * dvy + sz * dvz) * r;
+        finite = finite && isfinite(uu) && isfinite(vv);
+        umin = fminf(umin, uu); umax = fmaxf(umax, uu);
+        vmin = fminf(vmin, vv); vmax = fmaxf(vmax, vv);
+        dmin = fminf(dmin, den); dmax = fmaxf(dmax, den);
+    }
+    const float eps_u = 0.0078125f + 1e-6f * fmaxf(fabsf(umin), fabsf(umax));
+    const float eps_v = 0.0078125f + 1e-6f * fmaxf(fabsf(vmin), fabsf(vmax));
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    bp_finish_setup(P, ang, den_c, nu_c, nv_c, finite ? (double)(umin - eps_u) : nan, (double)(umax + eps_u), (double)(vmin - eps_v),
+                    (double)(vmax + eps_v), (double)dmin, (double)dmax, (double)hz, max_rows, max_cols, alt_cols, u_align,
+                    allow_rows3, rows_loop, out);
 }
 
 template <int OFF>
@@ -546,8 +596,13 @@ __global__ void __launch_bounds__(BP_THREADS) bp_kernel(const BPArgs P)
 constexpr int BP_TMA_PITCH = 68;
 constexpr int BP_TMA_PITCH_B = 60;  // alternative: consecutive rows start 4 banks *earlier*
 constexpr int BP_TMA_CONSUMERS = BP_TX * BP_TY;
-// BP_PUBLISHER (experiment): a second helper warp waits on the TMA barriers and publishes "angles ready" in a plain
-// shared-memory word, which the consumers poll with ld.shared (29 cycles) instead of mbarrier.try_wait (90+).
+// A second helper warp (the "publisher") waits on the TMA barriers and publishes "angles ready" in a plain
+// shared-memory word, which the consumers poll with ld.shared (29 cycles) instead of mbarrier.try_wait (90+ cycles,
+// paid by all eight consumer warps at the same moment): 48.5 -> 47.7 ms at cfg 3 (r02 GPU call 5).
+// -DBP_NO_PUBLISHER restores consumers that wait on the barrier themselves.
+#ifndef BP_NO_PUBLISHER
+#define BP_PUBLISHER 1
+#endif
 #ifdef BP_PUBLISHER
 constexpr int BP_TMA_HELPERS = 2;
 #else
@@ -563,7 +618,7 @@ __host__ __device__ constexpr size_t bp_tma_box_bytes(int zpt) { return (size_t)
 __host__ __device__ constexpr size_t bp_tma_stage_bytes(int zpt) { return (bp_tma_box_bytes(zpt) + 127) / 128 * 128; }
 __host__ __device__ constexpr size_t bp_tma_smem_bytes(int zpt)
 {
-    return bp_tma_stages(zpt) * (bp_tma_stage_bytes(zpt) + sizeof(BPLocal) + 16) + 128 + 16;
+    return bp_tma_stages(zpt) * (bp_tma_stage_bytes(zpt) + sizeof(BPLocal) + 16) + 128 + 16 + 2 * 20 * 33 * 4;
 }
 __host__ __device__ constexpr int bp_tma_min_ctas(int zpt) { return zpt >= 32 ? 2 : 3; }
 
@@ -622,12 +677,18 @@ bp_tma_kernel(const BPArgs P, const __grid_constant__ TensorMapPair tmaps)  // m
     // carve: [stages x footprint] [stages x BPLocal] [full barriers] [empty barriers];
     // the base is aligned by an offset (not an integer round trip) so that the compiler
     // keeps the shared state space of every pointer derived from it
+    // carve: [stages x footprint] [stages x BPLocal] [full barriers] [empty barriers] [ready] [producer scratch];
+    // the base is aligned by an offset (not an integer round trip) so that the compiler
+    // keeps the shared state space of every pointer derived from it
     unsigned char *base = bp_tma_smem + ((128u - (smem_u32(bp_tma_smem) & 127u)) & 127u);
     BPLocal *loc = reinterpret_cast<BPLocal *>(base + (size_t)STAGES * STAGE_BYTES);
     const uint32_t bufs = smem_u32(base);
+    const uint32_t loc0 = smem_u32(loc);
     const uint32_t full = smem_u32(loc + STAGES);
     const uint32_t empty = full + 8u * STAGES;
     const uint32_t ready = empty + 8u * STAGES;  // BP_PUBLISHER: number of angles whose footprint has landed
+    constexpr uint32_t PEND_BYTES = 20u * 33u * 4u;
+    const uint32_t pend = ready + 16u;           // producer scratch: 2 x (20 words x 33) (see the producer)
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -663,34 +724,66 @@ bp_tma_kernel(const BPArgs P, const __grid_constant__ TensorMapPair tmaps)  // m
 #endif
     if (warp == BP_TMA_CONSUMERS / 32) {
         // ------------------------------------------------------------ producer
-        const int group = lane >> 3, corner = lane & 7;
+        // A pass = 32 angles, one per lane (bp_setup_lane).  The lane's map goes to a transposed scratch table
+        // `pend` (word f of angle g at [f * 33 + g]: conflict-free both ways); when angle g's ring stage is free,
+        // lanes 0-19 copy its 20 words into the stage's BPLocal and lane 0 issues the TMA.  The next pass is set up
+        // right after the first angle of the current one has been issued - the moment the ring is full and the
+        // consumers have several angles of work queued - so issuing is never held up by the set-up arithmetic.
+        constexpr int LW = (int)(sizeof(BPLocal) / 4);
+        static_assert(sizeof(BPLocal) == 80, "BPLocal is copied as 20 words");
+        const float hxf = (float)hx, hyf = (float)hy, hzf = (float)hz;
+        auto setup_pass = [&](int a0, uint32_t pend_base, int &mode, int &u_lo, int &v_lo) {
+            BPLocal L;
+            bp_setup_lane(P, P.angles + min(a0 + lane, P.n_angles - 1), xc, yc, zc, hxf, hyf, hzf, WV, BP_TMA_PITCH, BP_TMA_PITCH_B, 4,
+                          !P.no_rows3, P.rows_loop, &L);
+            const uint32_t w[LW] = {__float_as_uint(L.au[0]), __float_as_uint(L.au[1]), __float_as_uint(L.au[2]), __float_as_uint(L.bu),
+                                    __float_as_uint(L.av[0]), __float_as_uint(L.av[1]), __float_as_uint(L.av[2]), __float_as_uint(L.bv),
+                                    __float_as_uint(L.ad[0]), __float_as_uint(L.ad[1]), __float_as_uint(L.ad[2]), __float_as_uint(L.bd),
+                                    (uint32_t)L.u_lo, (uint32_t)L.v_lo, (uint32_t)L.wu, (uint32_t)L.wv,
+                                    (uint32_t)L.mode, __float_as_uint(L.weight), (uint32_t)L.z_invariant, 0u};
+#pragma unroll
+            for (int f = 0; f < LW; ++f)
+                asm volatile("st.shared.u32 [%0], %1;" ::"r"(pend_base + 4u * (uint32_t)(f * 33 + lane)), "r"(w[f]) : "memory");
+            mode = L.mode; u_lo = L.u_lo; v_lo = L.v_lo;
+        };
         int s = 0;
         uint32_t parity = 1u;  // waiting on a fresh "empty" barrier with parity 1 passes at once
-        BPLocal L;
-        for (int a0 = 0; a0 < P.n_angles; a0 += 4) {
-            const int a = min(a0 + group, P.n_angles - 1);
-#ifdef BP_EXP_NOSETUP
-            if (a0 == 0)  // experiment: the set-up of the first four angles serves every angle (wrong results)
-#endif
-            bp_setup(P, P.angles + a, corner, xc, yc, zc, hx, hy, hz, WV, BP_TMA_PITCH, BP_TMA_PITCH_B, 4, !P.no_rows3, P.rows_loop, &L);  // valid in corner-0 lanes
-            for (int g = 0; g < 4 && a0 + g < P.n_angles; ++g) {
+        int mode = 0, u_lo = 0, v_lo = 0, mode_n = 0, u_lo_n = 0, v_lo_n = 0;
+        uint32_t pb = 0;
+        setup_pass(0, pend, mode, u_lo, v_lo);
+        __syncwarp();
+        for (int a0 = 0; a0 < P.n_angles; a0 += 32) {
+            const int n = min(32, P.n_angles - a0);
+            const uint32_t pend_cur = pend + pb * PEND_BYTES;
+            for (int g = 0; g < n; ++g) {
                 const int angle = a0 + g;
                 mbar_wait(empty + 8u * s, parity);
-                if (lane == g * 8) {
-                    loc[s] = L;
-                    if (L.mode == BP_SMEM || L.mode == BP_SMEM_CLAMP) {
+                const uint32_t loc_s = loc0 + (uint32_t)s * (uint32_t)sizeof(BPLocal);
+                if (lane < LW) {
+                    uint32_t v;
+                    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(pend_cur + 4u * (uint32_t)(lane * 33 + g)) : "memory");
+                    asm volatile("st.shared.u32 [%0], %1;" ::"r"(loc_s + 4u * (uint32_t)lane), "r"(v) : "memory");
+                }
+                const int mode_g = __shfl_sync(0xffffffffu, mode, g);
+                const int u_lo_g = __shfl_sync(0xffffffffu, u_lo, g), v_lo_g = __shfl_sync(0xffffffffu, v_lo, g);
+                __syncwarp();  // the stage's map is complete before the footprint is requested
+                if (lane == 0) {
+                    if (mode_g == BP_SMEM || mode_g == BP_SMEM_CLAMP) {
                         mbar_arrive_expect_tx(full + 8u * s, BOX_BYTES);
-                        tma_load_box_3d(bufs + (uint32_t)s * STAGE_BYTES, tmap, L.u_lo, angle, L.v_lo, full + 8u * s);
-                    } else if (L.mode == BP_SMEM_B) {
+                        tma_load_box_3d(bufs + (uint32_t)s * STAGE_BYTES, tmap, u_lo_g, angle, v_lo_g, full + 8u * s);
+                    } else if (mode_g == BP_SMEM_B) {
                         mbar_arrive_expect_tx(full + 8u * s, BOX_BYTES_B);
-                        tma_load_box_3d(bufs + (uint32_t)s * STAGE_BYTES, tmap + 1, L.u_lo, angle, L.v_lo, full + 8u * s);
+                        tma_load_box_3d(bufs + (uint32_t)s * STAGE_BYTES, tmap + 1, u_lo_g, angle, v_lo_g, full + 8u * s);
                     } else {
                         mbar_arrive(full + 8u * s);
                     }
                 }
-                __syncwarp();
                 if (++s == STAGES) { s = 0; parity ^= 1u; }
+                if (g == 0 && a0 + 32 < P.n_angles) setup_pass(a0 + 32, pend + (pb ^ 1u) * PEND_BYTES, mode_n, u_lo_n, v_lo_n);
             }
+            __syncwarp();
+            mode = mode_n; u_lo = u_lo_n; v_lo = v_lo_n;
+            pb ^= 1u;
         }
         return;
     }
@@ -723,7 +816,7 @@ bp_tma_kernel(const BPArgs P, const __grid_constant__ TensorMapPair tmaps)  // m
 #endif
         if (in_xy)
             bp_accumulate_angle<CONE, ZPT, BP_TMA_PITCH, BP_TMA_PITCH_B>(P, loc[s], bufs + (uint32_t)s * STAGE_BYTES, angle, dx, dy, dz0,
-                                                         row_pitch, acc);
+                                                                         row_pitch, acc);
         __syncwarp();
         if (lane == 0) mbar_arrive(empty + 8u * s);
         if (++s == STAGES) { s = 0; parity ^= 1u; }

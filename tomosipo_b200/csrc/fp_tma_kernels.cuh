@@ -110,7 +110,7 @@ __device__ __forceinline__ void fpt_slice_box(const FPRay (&c)[8], float t, floa
 
 // Consumer march over the hull slices [kA, kD) for pitch variant V (box_w[V] stays in a
 // uniform register, so the second tap row is addressed as [a0 + UR]).
-template <bool COLS, int V, int R>
+template <bool COLS, int V, int R, int SPS>
 __device__ __forceinline__ void fpt_consume(const FPTmaArgs &A, int kA, int kD, float t0, uint32_t ctrl, uint32_t full,
                                             uint32_t empty, int lane, const float2 *ap2, const float2 *cp2,
                                             const float2 (&aq2)[R / 2], const float2 (&cq2)[R / 2], float2 (&acc2)[R / 2])
@@ -120,7 +120,7 @@ __device__ __forceinline__ void fpt_consume(const FPTmaArgs &A, int kA, int kD, 
     const FPArgs &P = A.a;
     const float MAGIC = 12582912.0f;
     const uint32_t rs4 = A.row_stride4[V], so4 = A.slice_off4[V];
-    const int sps = A.sps;
+    constexpr int sps = SPS;
     float t = (float)kA + t0;
     int s = 0;
     uint32_t parity = 0u;
@@ -133,6 +133,7 @@ __device__ __forceinline__ void fpt_consume(const FPTmaArgs &A, int kA, int kD, 
             // independent fp32 operations per issue slot - the kernel is issue-bound): 10.5 instead
             // of 16 instructions per sample.  Every pair (.x, .y) = (row r, row r + 1).
             const float2 M2 = make_float2(MAGIC, MAGIC), NEG1 = make_float2(-1.0f, -1.0f);
+#pragma unroll
             for (int j = 0; j < sps; ++j) {  // a slice past the hull's end samples zeros (its box is staged all the same)
                 const float tj = t + (float)j;
                 const float2 t2 = make_float2(tj, tj);
@@ -169,7 +170,7 @@ __device__ __forceinline__ void fpt_consume(const FPTmaArgs &A, int kA, int kD, 
                     const float2 val = __ffma2_rn(wq2, __ffma2_rn(lo, NEG1, hi), lo);
                     acc2[h] = __fadd2_rn(acc2[h], val);
                 }
-                sb += so4;
+                if (SPS > 1) sb += so4;
             }
         } else {
             const int k_end = min(k + sps, P.n_m);
@@ -188,7 +189,7 @@ __device__ __forceinline__ void fpt_consume(const FPTmaArgs &A, int kA, int kD, 
     }
 }
 
-template <bool CONE, bool COLS, int R>
+template <bool CONE, bool COLS, int R, int SPS>
 __global__ void __launch_bounds__(FPT_THREADS, fpt_min_ctas(R))
 fp_tma_kernel(const FPTmaArgs A, const __grid_constant__ TensorMapPair tmaps)
 {
@@ -269,7 +270,7 @@ fp_tma_kernel(const FPTmaArgs A, const __grid_constant__ TensorMapPair tmaps)
         int s = 0;
         uint32_t parity = 1u;
         const int bw = A.box_w[variant];
-        const int sps = A.sps;
+        constexpr int sps = SPS;
         const int rs = (int)(A.row_stride4[variant] >> 2);  // words between q rows of a staged slice
         const uint32_t moff = A.magic_off[variant];
         const uint32_t box_bytes = (uint32_t)bw * (uint32_t)A.box_h * 4u * (uint32_t)sps;
@@ -346,8 +347,8 @@ fp_tma_kernel(const FPTmaArgs A, const __grid_constant__ TensorMapPair tmaps)
     }
     __syncthreads();
     const int kA = hull[0], kD = hull[1], variant = hull[2];
-    if (variant) fpt_consume<COLS, 1, R>(A, kA, kD, t0, ctrl, full, empty, lane, ap2, cp2, aq2, cq2, acc2);
-    else fpt_consume<COLS, 0, R>(A, kA, kD, t0, ctrl, full, empty, lane, ap2, cp2, aq2, cq2, acc2);
+    if (variant) fpt_consume<COLS, 1, R, SPS>(A, kA, kD, t0, ctrl, full, empty, lane, ap2, cp2, aq2, cq2, acc2);
+    else fpt_consume<COLS, 0, R, SPS>(A, kA, kD, t0, ctrl, full, empty, lane, ap2, cp2, aq2, cq2, acc2);
 
     if (slot_live && iu < P.det_u) {
 #pragma unroll

@@ -44,7 +44,11 @@ __device__ __forceinline__ void thin_hat_weights(float f, int c, float &w0, floa
 // A tap whose weight is exactly 0 (shifted window at a border, lanes outside their own slice interval) must not
 // contribute whatever it holds: 0 * Inf and 0 * NaN are NaN, while ASTRA's border mode and the tiled kernels read 0
 // there.  The load is predicated on the weight (one compare per weight, shared by the BT batch items).
+#ifdef THIN_NO_PREDICATE
+__device__ __forceinline__ float thin_tap(const float *s, float) { return __ldg(s); }
+#else
 __device__ __forceinline__ float thin_tap(const float *s, float w) { return w != 0.0f ? __ldg(s) : 0.0f; }
+#endif
 
 // grid: (det_u tiles of 32, angle tiles of 8, batch groups * det_v)
 template <bool CONE, int BT>

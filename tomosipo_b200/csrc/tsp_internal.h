@@ -67,6 +67,8 @@ struct DeviceState {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     // private stream-ordered memory pool of this (projector, device): per-call scratch and host-array staging
     cudaMemPool_t pool = nullptr;
+    size_t pool_keep = 0;       // current release threshold
+    size_t pool_keep_base = 0;  // the part kept for device-array calls (transposed-volume scratch)
 };
 
 }  // namespace tsp

@@ -324,8 +324,44 @@ static int create_projector_internal(const tsp_geometry *geometry, const int *ax
             f.d0[i] = na.dc[s] - 0.5 * g.det_cols * na.u[s] - 0.5 * g.det_rows * na.v[s];
         }
     }
-    for (auto &kv : groups) pr->groups.push_back(std::move(kv.second));
+    // Split every group by footprint width: the staged box of a launch is sized for its widest footprint (angles near
+    // the diagonals of the slice grid), and every CTA pays the TMA fill of that box - a third of the kernel's
+    // shared-memory traffic.  Near-axis angles get a launch of their own with a narrower box (and more ring stages).
+    for (auto &kv : groups) {
+        FPGroup &grp = kv.second;
+        const int nn[3] = {g.nx, g.ny, g.nz};
+        const int tile_v = 32;
+        std::vector<int> w(grp.angles.size());
+        int wmin = INT_MAX, wmax = 0;
+        for (size_t i = 0; i < grp.angles.size(); ++i) {
+            int h;
+            fp_pair_need(pr, grp.angles[i], -1, nn[grp.march], nn[grp.p_axis], nn[grp.q_axis], tile_v, w[i], h);
+            wmin = std::min(wmin, w[i]); wmax = std::max(wmax, w[i]);
+        }
+        int classes = 1;
+        // (measured at cfg 3 with two slices per stage: 1 class 42.9 ms, 2 classes 43.3, 3 classes 43.5 - the tails of
+        // the extra launches cost more than the narrower boxes save; kept as a tuning aid, TSP_FP_CLASSES=n)
+        if (const char *e = getenv("TSP_FP_CLASSES")) classes = std::max(1, std::min(4, atoi(e)));
+        if (grp.angles.size() < 96 || wmax - wmin < 12) classes = 1;
+        if (classes == 1) {
+            pr->groups.push_back(std::move(grp));
+            continue;
+        }
+        std::vector<FPGroup> sub(classes, grp);
+        for (auto &sg : sub) sg.angles.clear();
+        for (size_t i = 0; i < grp.angles.size(); ++i) {
+            const int c = std::min(classes - 1, (w[i] - wmin) * classes / (wmax - wmin + 1));
+            sub[c].angles.push_back(grp.angles[i]);
+        }
+        for (auto &sg : sub)
+            if (!sg.angles.empty()) pr->groups.push_back(std::move(sg));
+    }
     for (FPGroup &grp : pr->groups) plan_fp_tma_group(pr, grp);
+    if (getenv("TSP_DEBUG"))
+        for (const FPGroup &grp : pr->groups)
+            fprintf(stderr, "[tsp] plan: fp group march=%d transposed=%d cols=%d: %zu angles in %zu pairs, box need %dx%d, R=%d\n",
+                    grp.march, (int)grp.transposed, (int)grp.columns, grp.angles.size(), grp.pairs.size() / 2, grp.box_w, grp.box_h,
+                    grp.rows_per_thread);
     *out = pr;
     return TSP_OK;
 }
@@ -452,9 +488,11 @@ static int get_device_state(tsp_projector *pr, int device, DeviceState **out)
         props.location.id = device;
         if (cudaMemPoolCreate(&st.pool, &props) == cudaSuccess) {
             const int ny_pad = (pr->g.ny + 3) / 4 * 4;
-            uint64_t keep = (uint64_t)pr->g.nz * pr->g.nx * ny_pad * sizeof(float);
+            const uint64_t base = (uint64_t)pr->g.nz * pr->g.nx * ny_pad * sizeof(float);
+            uint64_t keep = base + base / 4 + ((uint64_t)32 << 20);
             if (const char *e = getenv("TSP_POOL_KEEP_MB")) keep = (uint64_t)std::max(0LL, atoll(e)) << 20;
             cudaMemPoolSetAttribute(st.pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            st.pool_keep = st.pool_keep_base = (size_t)base;
         } else {
             cudaGetLastError();
             st.pool = nullptr;  // falls back to the device's default pool, untouched
@@ -476,6 +514,21 @@ static cudaError_t pool_alloc(DeviceState *st, void **p, size_t bytes, cudaStrea
     return cudaMallocAsync(p, bytes, stream);
 }
 
+// Host-array calls stage whole arrays (or a ring of chunks) on the device: let the pool keep that much between calls,
+// so that an iterative loop over host arrays (the README SIRT of the reference) does not map and unmap gigabytes per
+// call (measured: 1807 -> 1127 GUPS end to end without this).  The bound is what this projector itself needs for one
+// call; tsp_projector_destroy gives everything back.
+static void pool_keep_at_least(DeviceState *st, size_t bytes)
+{
+    if (!st->pool || bytes <= st->pool_keep) return;
+    // the pool reserves whole 2 MB granules per allocation: a threshold equal to the bytes requested is exceeded by the
+    // rounding, and the excess block would be unmapped and mapped again on every call (measured: 1.8 instead of 0.65 ms
+    // per 18 MB host-array call, r02 GPU call 10) - keep a quarter plus 32 MB of slack
+    uint64_t keep = (uint64_t)bytes + bytes / 4 + ((uint64_t)32 << 20);
+    if (cudaMemPoolSetAttribute(st->pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess) st->pool_keep = bytes;
+    else cudaGetLastError();
+}
+
 // Per-call scratch from the projector's private pool, released (stream-ordered) on every exit path.
 struct PoolScratch {
     void *p = nullptr;
@@ -487,17 +540,17 @@ struct PoolScratch {
 static bool make_tensor_map_3d(const float *base, const uint64_t dims[3], const uint64_t stride_bytes[2],
                                const uint32_t box[3], TensorMapBlob *out);
 
-template <bool CONE, bool COLS, int R>
+template <bool CONE, bool COLS, int R, int SPS>
 static int launch_fp_tma_one(dim3 grid, size_t smem, cudaStream_t stream, const FPTmaArgs &A, const TensorMapPair &tmap)
 {
     static size_t configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 64 && configured[dev] < smem) {
-        CUDA_TRY(cudaFuncSetAttribute(fp_tma_kernel<CONE, COLS, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(fp_tma_kernel<CONE, COLS, R, SPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[dev] = smem;
     }
-    fp_tma_kernel<CONE, COLS, R><<<grid, FPT_THREADS, smem, stream>>>(A, tmap);
+    fp_tma_kernel<CONE, COLS, R, SPS><<<grid, FPT_THREADS, smem, stream>>>(A, tmap);
     return TSP_OK;
 }
 
@@ -536,7 +589,12 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
     PoolScratch scratch;
     const int ny_pad = (g.ny + 3) / 4 * 4;  // row pitch of the transposed copy: whole 16-byte units (TMA stride rule)
     if (need_t) {
-        CUDA_TRY(pool_alloc(st, &scratch.p, (size_t)batch * g.nz * g.nx * ny_pad * sizeof(float), stream));
+        const size_t scratch_bytes = (size_t)batch * g.nz * g.nx * ny_pad * sizeof(float);
+        if (scratch_bytes > st->pool_keep_base) {  // batched calls: keep the batch's scratch cached between calls
+            pool_keep_at_least(st, st->pool_keep + (scratch_bytes - st->pool_keep_base));
+            st->pool_keep_base = scratch_bytes;
+        }
+        CUDA_TRY(pool_alloc(st, &scratch.p, scratch_bytes, stream));
         scratch.stream = stream;
         vol_t = (float *)scratch.p;
         dim3 grid((g.nx + 31) / 32, (g.ny + 31) / 32, g.nz * batch), block(32, 8);  // batch items are contiguous planes
@@ -596,30 +654,38 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
             const bool middle = grp.march != 2;                // marching along the middle layout axis?
             const uint64_t dims[3] = {(uint64_t)P.n_p, (uint64_t)n_second, (uint64_t)g.nz};
             const uint64_t strides[2] = {(uint64_t)pitch_p * 4, (uint64_t)pitch_p * 4 * (uint64_t)n_second};
-            // slices per ring stage: 2 halves the per-slice hand-off (TSP_FP_SPS=1: one slice per stage)
-            int sps = 2;
+            // Slices per ring stage: 2 halves the per-slice hand-off (one barrier round trip, control word and TMA issue
+            // per stage; measured 46.7 -> 43.0 ms per FP at cfg 3); it needs three such stages in shared memory.
+            // TSP_FP_SPS=1: one slice per stage.
+            const int mult_of = middle ? 1 : 0;
+            int sps = 2, need_w = 0, box_h = 0;
+            int bw[2] = {0, 0};
             if (const char *e = getenv("TSP_FP_SPS")) sps = atoi(e) == 1 ? 1 : 2;
             if (P.n_m < 2) sps = 1;
-            // keep at least three ring stages in the shared-memory budget of the launch
-            if ((size_t)(grp.box_w + 36) * (grp.box_h + 1) * 2 * 4 * 3 > (size_t)(grp.rows_per_thread == 8 ? 108 : 72) * 1024) sps = 1;
-            // the footprint moves by at most one voxel per slice in p and in q (the marching axis dominates the ray)
-            const int need_w = (grp.box_w + (sps - 1) + 3) / 4 * 4, box_h = grp.box_h + (sps - 1);
-            // two pitch variants: box widths >= the needed width for which the row stride of a staged slice
-            // (box width x slices per stage when the marching axis is the middle tensor dimension) has a residue
-            // mod 32 banks of {4, 8} (column and row move together along a warp) or {24, 28} (opposite)
-            const int mult = middle ? sps : 1;
-            int bw[2] = {0, 0};
-            for (int w = need_w; w <= need_w + 32 && !(bw[0] && bw[1]); w += 4) {
-                const int r = (w * mult) & 31;
-                if (!bw[0] && (r == 4 || r == 8)) bw[0] = w;
-                if (!bw[1] && (r == 24 || r == 28)) bw[1] = w;
+            const size_t budget = (size_t)(grp.rows_per_thread == 8 ? 112 : 72) * 1024;
+            for (;; sps = 1) {
+                // the footprint moves by at most one voxel per slice in p and in q (the marching axis dominates the ray)
+                need_w = (grp.box_w + (sps - 1) + 3) / 4 * 4;
+                box_h = grp.box_h + (sps - 1);
+                // two pitch variants: box widths >= the needed width for which the row stride of a staged slice
+                // (box width x slices per stage when the marching axis is the middle tensor dimension) has a residue
+                // mod 32 banks of {4, 8} (column and row move together along a warp) or {24, 28} (opposite)
+                const int mult = mult_of ? sps : 1;
+                bw[0] = bw[1] = 0;
+                for (int w = need_w; w <= need_w + 32 && !(bw[0] && bw[1]); w += 4) {
+                    const int r = (w * mult) & 31;
+                    if (!bw[0] && (r == 4 || r == 8)) bw[0] = w;
+                    if (!bw[1] && (r == 24 || r == 28)) bw[1] = w;
+                }
+                if (getenv("TSP_FP_ONE_PITCH")) bw[0] = bw[1] = need_w;
+                // (the wider box costs L2 -> shared traffic, which has headroom: 26 % of the crossbar peak
+                // at cfg 3, while the shared-memory pipe is the busiest unit of this kernel)
+                if (!bw[0]) bw[0] = bw[1] ? bw[1] : need_w;
+                if (!bw[1]) bw[1] = bw[0];
+                if (bw[0] > 256 || bw[1] > 256) bw[0] = bw[1] = need_w;
+                const size_t stage = ((size_t)std::max(bw[0], bw[1]) * box_h * sps * 4 + 127) / 128 * 128 + 24;
+                if (sps == 1 || 3 * stage + 160 <= budget) break;
             }
-            if (getenv("TSP_FP_ONE_PITCH")) bw[0] = bw[1] = need_w;
-            // (the wider box costs L2 -> shared traffic, which has headroom: 26 % of the crossbar peak
-            // at cfg 3, while the shared-memory pipe is the busiest unit of this kernel)
-            if (!bw[0]) bw[0] = bw[1] ? bw[1] : need_w;
-            if (!bw[1]) bw[1] = bw[0];
-            if (bw[0] > 256 || bw[1] > 256) bw[0] = bw[1] = need_w;
             TensorMapPair slot;
             bool ok = box_h <= 256;
             for (int v = 0; v < 2 && ok; ++v) {
@@ -642,7 +708,7 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
                 T.march_is_middle = middle ? 1 : 0;
                 T.stage_bytes = ((uint32_t)std::max(bw[0], bw[1]) * box_h * sps * 4u + 127u) / 128u * 128u;
                 const int R = grp.rows_per_thread;
-                int stages = (int)(((R == 8 ? 108u : 72u) * 1024u) / (T.stage_bytes + 24u));
+                int stages = (int)(((R == 8 ? (sps == 2 ? 112u : 108u) : 72u) * 1024u) / (T.stage_bytes + 24u));
                 if (const char *e = getenv("TSP_FP_STAGES")) stages = atoi(e);
                 T.stages = std::max(2, std::min(stages, 12));
                 if (getenv("TSP_DEBUG"))
@@ -653,11 +719,13 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
                 dim3 tgrid((g.det_cols + FPT_TU - 1) / FPT_TU, (unsigned)(grp.pairs.size() / 2),
                            (g.det_rows + 4 * R - 1) / (4 * R));
                 int rc;
-#define TSP_FPT(C, L) (R == 8 ? launch_fp_tma_one<C, L, 8>(tgrid, smem, stream, T, slot) \
-                              : launch_fp_tma_one<C, L, 4>(tgrid, smem, stream, T, slot))
+#define TSP_FPT_S(C, L, S) (R == 8 ? launch_fp_tma_one<C, L, 8, S>(tgrid, smem, stream, T, slot) \
+                                   : launch_fp_tma_one<C, L, 4, S>(tgrid, smem, stream, T, slot))
+#define TSP_FPT(C, L) (sps == 2 ? TSP_FPT_S(C, L, 2) : TSP_FPT_S(C, L, 1))
                 if (cone) rc = grp.columns ? TSP_FPT(true, true) : TSP_FPT(true, false);
                 else rc = grp.columns ? TSP_FPT(false, true) : TSP_FPT(false, false);
 #undef TSP_FPT
+#undef TSP_FPT_S
                 if (rc) return rc;
                 ++pr->launches;
                 used_tma = 1;
@@ -1156,8 +1224,9 @@ struct PipeResources {
     cudaStream_t own_stream = nullptr;
     ~PipeResources()
     {
+        // (nothing to wait for when nothing was acquired: device-array calls stay asynchronous and capturable)
         for (void *b : bufs) cudaFreeAsync(b, stream);
-        if (stream || !bufs.empty()) cudaStreamSynchronize(stream);
+        if (!bufs.empty() || !events.empty()) cudaStreamSynchronize(stream);
         for (cudaEvent_t e : events) cudaEventDestroy(e);
         if (own_stream) cudaStreamDestroy(own_stream);
     }
@@ -1237,6 +1306,8 @@ static int project_host_chunks(tsp_projector *pr, int device, int direction, flo
     res.stream = user_stream;
     float *din[RING] = {nullptr, nullptr, nullptr}, *dout[RING] = {nullptr, nullptr, nullptr};
     const int nbuf = ring ? RING : 1;
+    pool_keep_at_least(st, st->pool_keep_base + (ring ? (size_t)RING * ((size_t)max_in * in_unit + (size_t)max_out * out_unit) * sizeof(float)
+                                                      : range_bytes));
     for (int i = 0; i < nbuf; ++i) {
         CUDA_TRY(res.alloc(st, &din[i], (size_t)(ring ? max_in : hi_in - lo_in) * in_unit));
         CUDA_TRY(res.alloc(st, &dout[i], (size_t)(ring ? max_out : hi_out - lo_out) * out_unit));
@@ -1412,6 +1483,7 @@ extern "C" int tsp_project(tsp_projector *pr, int direction, int additive, void 
     PipeResources res;  // releases the staging buffers on every exit path
     res.stream = stream;
     if (memory_kind == TSP_MEM_HOST) {
+        pool_keep_at_least(st, st->pool_keep_base + (nvox + npix) * batch * sizeof(float));
         CUDA_TRY(res.alloc(st, &dvol, nvox * batch));
         CUDA_TRY(res.alloc(st, &dproj, npix * batch));
         // inputs, and the destination too when accumulating
@@ -1588,4 +1660,64 @@ extern "C" int tsp_fdk_stage(tsp_projector *pr, int stage, const void *in, void 
     ++pr->launches;
     CUDA_TRY(cudaGetLastError());
     return TSP_OK;
+}
+
+// ------------------------------------------------------ pinned host buffers --
+// Page-locked host buffers for the arrays the host-array path itself creates (operator outputs, the float32 copies
+// of float64 inputs: tomosipo_b200/links/numpy.py).  cudaMemcpyAsync from / to pageable memory is staged through a
+// driver bounce buffer and does not overlap anything; the README loop of the reference (README.md:150-164, BASELINE
+// configs[0]) allocates a fresh output per call, so freed buffers are kept on a size-keyed free list (bounded by
+// TSP_PINNED_CACHE_MB, default 1024) - cudaHostAlloc itself costs about as much as the pageable copy it avoids.
+namespace {
+std::mutex g_pin_mu;
+std::multimap<size_t, void *> g_pin_free;      // size -> buffer
+std::map<void *, size_t> g_pin_live;           // buffer -> size
+size_t g_pin_cached = 0;
+size_t pin_round(size_t b) { return (b + 65535) / 65536 * 65536; }
+}  // namespace
+
+extern "C" void *tsp_host_alloc(size_t bytes)
+{
+    if (bytes == 0 || tsp_device_count() == 0) return nullptr;
+    const size_t sz = pin_round(bytes);
+    {
+        std::lock_guard<std::mutex> lock(g_pin_mu);
+        auto it = g_pin_free.find(sz);
+        if (it != g_pin_free.end()) {
+            void *p = it->second;
+            g_pin_free.erase(it);
+            g_pin_cached -= sz;
+            g_pin_live[p] = sz;
+            return p;
+        }
+    }
+    void *p = nullptr;
+    if (cudaHostAlloc(&p, sz, cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        return nullptr;
+    }
+    std::lock_guard<std::mutex> lock(g_pin_mu);
+    g_pin_live[p] = sz;
+    return p;
+}
+
+extern "C" void tsp_host_free(void *p)
+{
+    if (!p) return;
+    size_t sz = 0;
+    {
+        std::lock_guard<std::mutex> lock(g_pin_mu);
+        auto it = g_pin_live.find(p);
+        if (it == g_pin_live.end()) return;  // not ours
+        sz = it->second;
+        g_pin_live.erase(it);
+        size_t cap = (size_t)1024 << 20;
+        if (const char *e = getenv("TSP_PINNED_CACHE_MB")) cap = (size_t)std::max(0LL, atoll(e)) << 20;
+        if (g_pin_cached + sz <= cap) {
+            g_pin_free.emplace(sz, p);
+            g_pin_cached += sz;
+            return;
+        }
+    }
+    cudaFreeHost(p);
 }

@@ -107,6 +107,7 @@ class ShardedOperator:
         self._partial = None
         self._chunk_ops = None
         self._comm_stream = None
+        self._fp_blocks = False   # not planned yet (None: planned, no row-blocked forward projection)
         self._transpose = _ShardedTranspose(self)
         # The exchange only overlaps the kernels if its CTAs are scheduled ahead of the backprojector's
         # queued ones: NCCL must run on high-priority streams.  With the default group that is a
@@ -248,6 +249,54 @@ class ShardedOperator:
         if comm is not None:
             compute.wait_stream(comm)
 
+    # ------------------------------------------------- row-blocked forward --
+    def _fp_row_blocks(self):
+        """Plan of the overlapped forward projection: ``(gather order, [(ready, v0, v1, z0, z1, operator)])``.
+
+        A block of detector rows only sees the slices its rays can reach (for a cone beam: a z range about as tall
+        as the block), so its forward projection can start as soon as the z-chunks covering that range have been
+        all-gathered - the remaining chunks arrive behind its kernels.  The row blocks and their slice ranges are the
+        ones the library plans for host arrays (``tsp_projector_host_plan``, bounds checked in
+        tests/test_host_plan.py); chunks are gathered from the outside in, because the outermost rows need the
+        fewest slices.  ``ready`` = index in the gather order of the last chunk a block waits for.  ``None`` when
+        the rank-local operator is not the library's or the problem is too small to be cut."""
+        if self._fp_blocks is not False:
+            return self._fp_blocks
+        self._fp_blocks = None
+        proj = getattr(self.local, "astra_projector", None)
+        if self.world == 1 or self.chunks < 2 or proj is None or not hasattr(proj, "host_plan") or os.environ.get("TSP_SHARD_NO_FP_BLOCKS"):
+            return None
+        from . import _backend
+
+        plan = proj.host_plan(_backend.FP)
+        if len(plan) < 2:
+            return None
+        order = []
+        lo, hi = 0, self.chunks - 1
+        while lo <= hi:                                   # outside in: 0, K-1, 1, K-2, ...
+            order.append(lo)
+            if hi != lo:
+                order.append(hi)
+            lo, hi = lo + 1, hi - 1
+        pos = {c: i for i, c in enumerate(order)}
+        blocks = []
+        for z0, z1, v0, v1 in sorted(plan, key=lambda e: e[2]):
+            need = [c for c in range(self.chunks) if self.chunk_bounds(c)[0] < z1 and self.chunk_bounds(c)[1] > z0]
+            ready = max(pos[c] for c in need) if need else 0
+            if blocks and blocks[-1][0] == ready and blocks[-1][2] == v0:   # merge neighbours that start together
+                r, a, _, za, zb = blocks[-1]
+                blocks[-1] = (r, a, v1, min(za, z0), max(zb, z1))
+            else:
+                blocks.append((ready, v0, v1, z0, z1))
+        if len(blocks) < 2 or min(b[0] for b in blocks) == len(order) - 1:
+            return None                                   # nothing can start early
+        out = []
+        for ready, v0, v1, z0, z1 in sorted(blocks):
+            op = self._make_local(self.volume_geometry[z0:z1], self.local_pg[:, v0:v1, :])
+            out.append((ready, v0, v1, z0, z1, op))
+        self._fp_blocks = (order, out)
+        return self._fp_blocks
+
     # ------------------------------------------------------------ operator --
     def __call__(self, x_slab, out=None):
         """``y_block = A[angle block] (all_gather(x_slab))``."""
@@ -257,11 +306,30 @@ class ShardedOperator:
             return self.local(x_slab, out=out)
         full = self._full_volume(x_slab)
         x_slab = x_slab.contiguous()
-        for c in range(self.chunks):
-            self._all_gather_chunk(full, x_slab, c)
         if out is None:
             out = torch.empty(self.proj_shape, dtype=torch.float32, device=x_slab.device)
-        self.local(full[: self.vol_shape[0]], out=out)
+        compute, comm = self._streams(x_slab)
+        plan = self._fp_row_blocks() if (comm is not None and out.is_contiguous()) else None
+        if plan is None:
+            for c in range(self.chunks):
+                self._all_gather_chunk(full, x_slab, c)
+            self.local(full[: self.vol_shape[0]], out=out)
+            return out
+        # chunk-wise all-gather on the communication stream; every row block starts behind the chunks it needs
+        order, blocks = plan
+        comm.wait_stream(compute)                          # earlier readers of `full`, the producer of x_slab
+        arrived = []
+        with torch.cuda.stream(comm):
+            for c in order:
+                self._all_gather_chunk(full, x_slab, c)
+                ev = torch.cuda.Event()
+                ev.record(comm)
+                arrived.append(ev)
+        for ready, v0, v1, z0, z1, op in blocks:
+            compute.wait_event(arrived[ready])
+            op(full[z0:z1], out=out[v0:v1])
+        compute.wait_event(arrived[-1])                    # `full` is complete for whoever reads it next
+        x_slab.record_stream(comm)
         return out
 
     def _bp(self, y_block, out=None):

@@ -8,6 +8,14 @@ import cupy
 from .base import Link, RawBuffer, backends
 
 
+def _torch_link_class():
+    """TorchLink if PyTorch has been imported by the application, else None (never imports torch itself)."""
+    import sys
+
+    mod = sys.modules.get("tomosipo_b200.links.torch")
+    return getattr(mod, "TorchLink", None)
+
+
 class CupyLink(Link):
     """Wraps a C-contiguous float32 ``cupy.ndarray``."""
 
@@ -46,6 +54,12 @@ class CupyLink(Link):
     def __compatible_with__(self, other):
         if isinstance(other, CupyLink):
             return self._data.device == other._data.device
+        # CUDA tensors of PyTorch on the same GPU (a TODO in the reference, links/cupy.py:66-72): both are plain
+        # device pointers to the C ABI; direct_project orders the two libraries' current streams
+        torch_link = _torch_link_class()
+        if torch_link is not None and isinstance(other, torch_link):
+            t = other.data
+            return bool(t.is_cuda) and t.device.index == self._data.device.id
         return NotImplemented
 
     @property

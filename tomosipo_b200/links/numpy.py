@@ -4,7 +4,18 @@ from contextlib import contextmanager
 
 import numpy as np
 
+from .. import _backend
 from .base import Link, RawBuffer, backends
+
+
+def _pinned_like(shape, dtype, fill=None):
+    """Array for data this link creates itself: page-locked when large (float32 only), see _backend.pinned_empty."""
+    if np.dtype(dtype) != np.float32:
+        return np.empty(shape, dtype=dtype) if fill is None else np.full(shape, fill, dtype=dtype)
+    out = _backend.pinned_empty(shape, np.float32)
+    if fill is not None:
+        out[...] = fill
+    return out
 
 
 class NumpyLink(Link):
@@ -27,7 +38,9 @@ class NumpyLink(Link):
                 f"The type has been Automatically converted. "
                 f"Use `ts.link(x.astype(np.float32))' to inhibit this warning. "
             )
-            arr = arr.astype(np.float32)
+            conv = _pinned_like(arr.shape, np.float32)
+            conv[...] = arr
+            arr = conv
         if not (arr.flags["C_CONTIGUOUS"] and arr.flags["ALIGNED"]):
             warnings.warn(
                 f"The parameter initial_value should be C_CONTIGUOUS and ALIGNED. "
@@ -67,13 +80,13 @@ class NumpyLink(Link):
         yield
 
     def new_zeros(self, shape):
-        return NumpyLink(shape, np.zeros(shape, dtype=self._data.dtype))
+        return NumpyLink(shape, _pinned_like(shape, self._data.dtype, 0.0))
 
     def new_full(self, shape, value):
-        return NumpyLink(shape, np.full(shape, value, dtype=self._data.dtype))
+        return NumpyLink(shape, _pinned_like(shape, self._data.dtype, value))
 
     def new_empty(self, shape):
-        return NumpyLink(shape, np.empty(shape, dtype=self._data.dtype))
+        return NumpyLink(shape, _pinned_like(shape, self._data.dtype))
 
     def clone(self):
         return NumpyLink(self._data.shape, np.copy(self._data))
