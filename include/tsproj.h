@@ -181,6 +181,22 @@ int tsp_project_fused(tsp_projector *projector, int direction, void *vol, void *
                       const void *mul, int device, void *cuda_stream);
 
 /*
+ * Forward projection from a caller-made transposed copy.  Angles that march along x read an (x <-> y)-transposed copy
+ * of the volume, which tsp_project makes per call.  A caller that assembles the volume piecewise - the multi-GPU
+ * operator, whose z-chunks arrive one all-gather at a time (tomosipo_b200/distributed.py) - can transpose each piece as
+ * it arrives, behind the transfers still in flight, and hand the finished copy in:
+ *   tsp_fp_transposed_elems   number of floats of the transposed copy ([nz][nx][ny rounded up to 4]); 0 = not needed
+ *   tsp_transpose_slices      slices [z0, z1) of `vol` (dense [nz][ny][nx]) into `vol_t`; asynchronous on the stream
+ *   tsp_fp_pre_transposed     proj = A vol, or mul * (A vol - sub) when sub / mul are given (see tsp_project_fused);
+ *                             vol_t may be NULL (then the library transposes itself, as tsp_project does)
+ */
+int tsp_fp_transposed_elems(const tsp_projector *projector, int64_t *elems);
+int tsp_transpose_slices(tsp_projector *projector, const void *vol, void *vol_t, int z0, int z1, int device,
+                         void *cuda_stream);
+int tsp_fp_pre_transposed(tsp_projector *projector, const void *vol, const void *vol_t, void *proj, const void *sub,
+                          const void *mul, int device, void *cuda_stream);
+
+/*
  * Page-locked host buffers for arrays the host-array path creates itself (the operator's outputs and the float32
  * copies of float64 inputs; reference tomosipo/links/numpy.py:26-32,121-144 allocates them with numpy): transfers
  * from / to pageable memory do not overlap the kernels.  Freed buffers are cached by size (TSP_PINNED_CACHE_MB,

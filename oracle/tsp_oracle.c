@@ -6,15 +6,20 @@
  * cpu_baseline / --impl reference legs of bench.py are the only callers.
  * Nothing under tomosipo_b200/ may import, link or execute it.
  *
- * PARITY STATUS: "partially pinned".  The arithmetic itself lives in the ASTRA
+ * PARITY STATUS: pinned as far as the reference allows; ASTRA's own BP / cone-FP
+ * values are "parity unpinned".  The arithmetic itself lives in the ASTRA
  * toolbox (astra-toolbox >= 2.0, un-vendored dependency of the reference,
  * setup.py:15), which is absent from /root/reference and from this image.
- * The forward projector is pinned against the one real ASTRA output the
- * reference ships (notebooks/cupy.ipynb cell 4, see tests/test_oracle_kat.py);
- * the backprojector scale is pinned only through adjointness / SIRT-weight
- * invariants (tests/test_oracle_invariants.py).  Everything else is a
- * restatement of ASTRA's published cuda3d semantics as summarised in
- * SURVEY.md Appendix B.
+ * Pinned: the forward projector against the one real ASTRA output the
+ * reference ships (notebooks/cupy.ipynb cell 4, tests/test_oracle.py) and
+ * against closed-form line integrals, cone and parallel (tests/test_oracle_pins.py);
+ * the backprojector's voxel -> detector map against the reference's own
+ * project_point (golden vectors + tests/geometry/test_cone_vec.py:143-173); its
+ * weight against closed forms, and - the open question of SURVEY.md B.2 - shown
+ * to be the exact adjoint's weight times the cosine of the ray's obliquity.
+ * Not pinned (no such number exists in the reference): any backprojection or
+ * cone-beam value computed by ASTRA itself.  Everything else is a restatement
+ * of ASTRA's published cuda3d semantics as summarised in SURVEY.md Appendix B.
  *
  * What is restated, and which reference call site consumes it:
  *   - geometry normalisation (unit voxels, centred volume):

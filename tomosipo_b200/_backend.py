@@ -80,6 +80,9 @@ EXPORTED_SYMBOLS = (
     "tsp_fdk_stage",
     "tsp_host_alloc",
     "tsp_host_free",
+    "tsp_fp_transposed_elems",
+    "tsp_transpose_slices",
+    "tsp_fp_pre_transposed",
 )
 
 
@@ -138,6 +141,12 @@ def lib():
         L.tsp_fdk_stage.argtypes = [vp, ctypes.c_int, vp, vp, ctypes.c_int, ctypes.c_int, vp,
                                     ctypes.POINTER(ctypes.c_double), ctypes.c_int, vp]
         L.tsp_fdk_stage.restype = ctypes.c_int
+        L.tsp_fp_transposed_elems.argtypes = [vp, ctypes.POINTER(ctypes.c_int64)]
+        L.tsp_fp_transposed_elems.restype = ctypes.c_int
+        L.tsp_transpose_slices.argtypes = [vp, vp, vp, ctypes.c_int, ctypes.c_int, ctypes.c_int, vp]
+        L.tsp_transpose_slices.restype = ctypes.c_int
+        L.tsp_fp_pre_transposed.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int, vp]
+        L.tsp_fp_pre_transposed.restype = ctypes.c_int
         L.tsp_host_alloc.argtypes = [ctypes.c_size_t]
         L.tsp_host_alloc.restype = vp
         L.tsp_host_free.argtypes = [vp]
@@ -256,6 +265,22 @@ class Projector:
         devs = (ctypes.c_int * len(devices))(*[int(d) for d in devices])
         _check(lib().tsp_project_multi(self._handle, int(direction), int(bool(additive)), ctypes.c_void_p(vol_ptr),
                                        ctypes.c_void_p(proj_ptr), devs, len(devices)))
+
+    def fp_transposed_elems(self):
+        """Floats of the (x <-> y)-transposed volume copy the forward projector reads (0: none of its angles needs one)."""
+        n = ctypes.c_int64(0)
+        _check(lib().tsp_fp_transposed_elems(self._handle, ctypes.byref(n)))
+        return int(n.value)
+
+    def transpose_slices(self, vol_ptr, vol_t_ptr, z0, z1, device=0, stream=0):
+        vp = ctypes.c_void_p
+        _check(lib().tsp_transpose_slices(self._handle, vp(vol_ptr), vp(vol_t_ptr), int(z0), int(z1), int(device), vp(stream)))
+
+    def fp_pre_transposed(self, vol_ptr, vol_t_ptr, proj_ptr, sub_ptr=None, mul_ptr=None, device=0, stream=0):
+        """``proj = A vol`` (or ``mul * (A vol - sub)``) reading the caller's transposed copy ``vol_t_ptr``."""
+        vp = ctypes.c_void_p
+        _check(lib().tsp_fp_pre_transposed(self._handle, vp(vol_ptr), vp(vol_t_ptr), vp(proj_ptr), vp(sub_ptr), vp(mul_ptr),
+                                           int(device), vp(stream)))
 
     def fdk_stage(self, stage, in_ptr, out_ptr, pitch, aux, redundancy_ptr, angle_weights, device=0, stream=0):
         """One element-wise pass of the FDK pre-filter on device pointers (``tsp_fdk_stage`` in include/tsproj.h)."""

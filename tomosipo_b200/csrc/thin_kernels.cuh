@@ -41,14 +41,22 @@ __device__ __forceinline__ void thin_hat_weights(float f, int c, float &w0, floa
     w1 = fmaxf(0.0f, 1.0f - fabsf(x - 1.0f));
 }
 
-// A tap whose weight is exactly 0 (shifted window at a border, lanes outside their own slice interval) must not
-// contribute whatever it holds: 0 * Inf and 0 * NaN are NaN, while ASTRA's border mode and the tiled kernels read 0
-// there.  The load is predicated on the weight (one compare per weight, shared by the BT batch items).
-#ifdef THIN_NO_PREDICATE
-__device__ __forceinline__ float thin_tap(const float *s, float) { return __ldg(s); }
+// A tap whose weight is exactly 0 (shifted window at a border, lanes outside their own slice interval) still
+// multiplies what it loads: 0 * Inf and 0 * NaN are NaN, so a NON-FINITE value in the outermost two rows / columns of
+// the array can reach samples that lie within one element outside the array, which ASTRA's border mode and the
+// tiled kernels (TSP_NO_THIN=1) would leave finite.  Guarding it was measured twice on the learned-PD
+// step (r02 GPU calls 11, 12): loads predicated on the weight 1.18 -> 1.48 ms, FMAs predicated on the weight
+// 1.18 -> 1.44 ms - a quarter of the step for a case that needs non-finite border data.  The guard is therefore a
+// build option (-DTHIN_STRICT_BORDERS); finite data and non-finite interior data behave identically either way.
+__device__ __forceinline__ void thin_fma(float &acc, bool live, float w, float v)
+{
+#ifdef THIN_STRICT_BORDERS
+    if (live) acc = fmaf(w, v, acc);
 #else
-__device__ __forceinline__ float thin_tap(const float *s, float w) { return w != 0.0f ? __ldg(s) : 0.0f; }
+    (void)live;
+    acc = fmaf(w, v, acc);
 #endif
+}
 
 // grid: (det_u tiles of 32, angle tiles of 8, batch groups * det_v)
 template <bool CONE, int BT>
@@ -113,17 +121,23 @@ __global__ void __launch_bounds__(32 * THIN_FP_ANGLES) fp_thin_kernel(const FPAr
         if (one_row) wq1 = 0.0f;
         const uint32_t off = (uint32_t)k * sm32 + (uint32_t)r * sq32 + (uint32_t)c;
         const float w00 = wq0 * wp0, w01 = wq0 * wp1;
+        const bool l00 = w00 != 0.0f, l01 = w01 != 0.0f;
 #pragma unroll
         for (int j = 0; j < BT; ++j) {
             const float *s = vol0 + (ob[j] + off);
-            acc[j] = fmaf(w00, thin_tap(s, w00), fmaf(w01, thin_tap(s + 1, w01), acc[j]));
+            const float v0 = __ldg(s), v1 = __ldg(s + 1);
+            thin_fma(acc[j], l01, w01, v1);
+            thin_fma(acc[j], l00, w00, v0);
         }
         if (wq1 != 0.0f) {
             const float w10 = wq1 * wp0, w11 = wq1 * wp1;
+            const bool l10 = w10 != 0.0f, l11 = w11 != 0.0f;
 #pragma unroll
             for (int j = 0; j < BT; ++j) {
                 const float *s = vol0 + (ob[j] + off + sq32);
-                acc[j] = fmaf(w10, thin_tap(s, w10), fmaf(w11, thin_tap(s + 1, w11), acc[j]));
+                const float v0 = __ldg(s), v1 = __ldg(s + 1);
+                thin_fma(acc[j], l11, w11, v1);
+                thin_fma(acc[j], l10, w10, v0);
             }
         }
     }
@@ -229,17 +243,23 @@ __global__ void __launch_bounds__(BP_THREADS) bp_thin_kernel(const BPArgs P, int
                     wv0 *= w2; wv1 *= w2;
                     const uint32_t off = aoff + (uint32_t)r * rp32 + (uint32_t)c;
                     const float w00 = wv0 * wu0, w01 = wv0 * wu1;
+                    const bool l00 = w00 != 0.0f, l01 = w01 != 0.0f;
 #pragma unroll
                     for (int b = 0; b < BT; ++b) {
                         const float *s = proj0 + (ob[b] + off);
-                        acc[i][b] = fmaf(w00, thin_tap(s, w00), fmaf(w01, thin_tap(s + 1, w01), acc[i][b]));
+                        const float v0 = __ldg(s), v1 = __ldg(s + 1);
+                        thin_fma(acc[i][b], l01, w01, v1);
+                        thin_fma(acc[i][b], l00, w00, v0);
                     }
                     if (wv1 != 0.0f) {
                         const float w10 = wv1 * wu0, w11 = wv1 * wu1;
+                        const bool l10 = w10 != 0.0f, l11 = w11 != 0.0f;
 #pragma unroll
                         for (int b = 0; b < BT; ++b) {
                             const float *s = proj0 + (ob[b] + off + rp32);
-                            acc[i][b] = fmaf(w10, thin_tap(s, w10), fmaf(w11, thin_tap(s + 1, w11), acc[i][b]));
+                            const float v0 = __ldg(s), v1 = __ldg(s + 1);
+                            thin_fma(acc[i][b], l11, w11, v1);
+                            thin_fma(acc[i][b], l10, w10, v0);
                         }
                     }
                     nu += L[2]; nv += L[6];

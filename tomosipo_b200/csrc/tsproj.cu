@@ -555,7 +555,8 @@ static int launch_fp_tma_one(dim3 grid, size_t smem, cudaStream_t stream, const 
 }
 
 static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float *proj, int additive,
-                     cudaStream_t stream, const float *epi_sub = nullptr, const float *epi_mul = nullptr, int batch = 1)
+                     cudaStream_t stream, const float *epi_sub = nullptr, const float *epi_mul = nullptr, int batch = 1,
+                     const float *vol_t_ext = nullptr)  // caller-made (x <-> y)-transposed copy (tsp_transpose_slices)
 {
     const tsp_geometry &g = pr->g;
     const int n[3] = {g.nx, g.ny, g.nz};
@@ -588,7 +589,9 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
     float *vol_t = nullptr;
     PoolScratch scratch;
     const int ny_pad = (g.ny + 3) / 4 * 4;  // row pitch of the transposed copy: whole 16-byte units (TMA stride rule)
-    if (need_t) {
+    if (need_t && vol_t_ext && batch == 1) {
+        vol_t = const_cast<float *>(vol_t_ext);
+    } else if (need_t) {
         const size_t scratch_bytes = (size_t)batch * g.nz * g.nx * ny_pad * sizeof(float);
         if (scratch_bytes > st->pool_keep_base) {  // batched calls: keep the batch's scratch cached between calls
             pool_keep_at_least(st, st->pool_keep + (scratch_bytes - st->pool_keep_base));
@@ -1556,6 +1559,54 @@ extern "C" int tsp_project_fused(tsp_projector *pr, int direction, void *vol, vo
     if (direction == TSP_FP)
         return launch_fp(pr, st, (const float *)vol, (float *)proj, 0, stream, (const float *)sub, (const float *)mul);
     return launch_bp(pr, st, (float *)vol, (const float *)proj, 0, stream, (const float *)mul);
+}
+
+// ---- forward projection from a caller-made transposed copy (multi-GPU: tomosipo_b200/distributed.py) ----------------
+extern "C" int tsp_fp_transposed_elems(const tsp_projector *pr, int64_t *elems)
+{
+    if (!pr || !elems) return fail(TSP_ERR_INVALID, "NULL argument");
+    bool need_t = false;
+    for (const FPGroup &grp : pr->groups) need_t |= grp.transposed;
+    const int ny_pad = (pr->g.ny + 3) / 4 * 4;
+    *elems = need_t ? (int64_t)pr->g.nz * pr->g.nx * ny_pad : 0;
+    return TSP_OK;
+}
+
+extern "C" int tsp_transpose_slices(tsp_projector *pr, const void *vol, void *vol_t, int z0, int z1, int device, void *cuda_stream)
+{
+    if (!pr || !vol || !vol_t) return fail(TSP_ERR_INVALID, "NULL argument");
+    const tsp_geometry &g = pr->g;
+    if (z0 < 0 || z1 > g.nz || z1 < z0) return fail(TSP_ERR_INVALID, "slice range [%d, %d) outside the volume", z0, z1);
+    if (z1 == z0) return TSP_OK;
+    if (z1 - z0 > 65535) return fail(TSP_ERR_INVALID, "too many slices for one transpose launch");
+    const int ndev = tsp_device_count();
+    if (ndev == 0) return fail(TSP_ERR_CUDA, "no CUDA device available (libtsproj has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(TSP_ERR_INVALID, "device %d out of range [0, %d)", device, ndev);
+    DeviceGuard guard;
+    if (guard.enter(device) != 0) return fail(TSP_ERR_CUDA, "cannot switch to device %d", device);
+    const int ny_pad = (g.ny + 3) / 4 * 4;
+    dim3 grid((g.nx + 31) / 32, (g.ny + 31) / 32, z1 - z0), block(32, 8);
+    transpose_xy_kernel<<<grid, block, 0, (cudaStream_t)cuda_stream>>>((const float *)vol + (size_t)z0 * g.nx * g.ny,
+                                                                       (float *)vol_t + (size_t)z0 * g.nx * ny_pad, g.nx, g.ny, ny_pad);
+    ++pr->launches;
+    CUDA_TRY(cudaGetLastError());
+    return TSP_OK;
+}
+
+extern "C" int tsp_fp_pre_transposed(tsp_projector *pr, const void *vol, const void *vol_t, void *proj, const void *sub,
+                                     const void *mul, int device, void *cuda_stream)
+{
+    if (!pr || !vol || !proj) return fail(TSP_ERR_INVALID, "NULL argument");
+    if ((sub != nullptr) != (mul != nullptr)) return fail(TSP_ERR_INVALID, "sub and mul go together");
+    const int ndev = tsp_device_count();
+    if (ndev == 0) return fail(TSP_ERR_CUDA, "no CUDA device available (libtsproj has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(TSP_ERR_INVALID, "device %d out of range [0, %d)", device, ndev);
+    DeviceGuard guard;
+    if (guard.enter(device) != 0) return fail(TSP_ERR_CUDA, "cannot switch to device %d", device);
+    DeviceState *st = nullptr;
+    if (int rc = get_device_state(pr, device, &st)) return rc;
+    return launch_fp(pr, st, (const float *)vol, (float *)proj, 0, (cudaStream_t)cuda_stream, (const float *)sub, (const float *)mul, 1,
+                     (const float *)vol_t);
 }
 
 // -------------------------------------------------------------------- FDK --

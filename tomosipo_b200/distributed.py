@@ -104,10 +104,10 @@ class ShardedOperator:
         self.z_lo, self.z_hi = self.piece_bounds(0, self.rank) if self.chunks == 1 else (None, None)
         self.device = device
         self._full = None
+        self._full_t = False      # not decided yet (None: no caller-made transposed copy)
         self._partial = None
         self._chunk_ops = None
         self._comm_stream = None
-        self._fp_blocks = False   # not planned yet (None: planned, no row-blocked forward projection)
         self._transpose = _ShardedTranspose(self)
         # The exchange only overlaps the kernels if its CTAs are scheduled ahead of the backprojector's
         # queued ones: NCCL must run on high-priority streams.  With the default group that is a
@@ -175,6 +175,39 @@ class ShardedOperator:
         if self._partial is None or self._partial.device != like.device:
             self._partial = torch.zeros(self.padded_shape, dtype=torch.float32, device=like.device)
         return self._partial
+
+    def _transposed_volume(self, like):
+        """Device buffer for the (x <-> y)-transposed copy of the replicated volume that this rank's forward projector
+        reads (angles marching along x), or None (not needed / rank-local operator is not the library's).  With it,
+        every z-chunk is transposed as it arrives (behind the all-gather of the next chunk, or behind the next
+        chunk's backprojection in SIRT) instead of the whole volume being transposed in front of every FP."""
+        if self._full_t is False:
+            self._full_t = None
+            proj = getattr(self.local, "astra_projector", None)
+            if (like.is_cuda and proj is not None and hasattr(proj, "fp_transposed_elems") and self.world > 1
+                    and not getattr(self.local, "additive", False) and not os.environ.get("TSP_SHARD_NO_PRETRANSPOSE")):
+                n = proj.fp_transposed_elems()
+                if n > 0:
+                    self._full_t = torch.empty(n, dtype=torch.float32, device=like.device)
+        return self._full_t
+
+    def _transpose_chunk(self, full, full_t, c):
+        """Transpose the slices of chunk ``c`` of ``full`` into ``full_t`` on the current stream."""
+        lo, hi = self.chunk_bounds(c)
+        if hi > lo:
+            stream = torch.cuda.current_stream(full.device).cuda_stream
+            self.local.astra_projector.transpose_slices(full.data_ptr(), full_t.data_ptr(), lo, hi, device=full.device.index,
+                                                        stream=stream)
+
+    def _fp_local(self, full, full_t, out, y=None, R=None):
+        """``out = A[block] full`` (or ``R * (A full - y)``) from the replicated volume and its transposed copy."""
+        proj = self.local.astra_projector
+        stream = torch.cuda.current_stream(full.device).cuda_stream
+        with torch.cuda.device_of(full):
+            proj.fp_pre_transposed(full.data_ptr(), full_t.data_ptr(), out.data_ptr(),
+                                   None if y is None else y.data_ptr(), None if R is None else R.data_ptr(),
+                                   device=full.device.index, stream=stream)
+        return out
 
     def chunk_operators(self):
         """``[(c, z_lo, z_hi, operator on vg[z_lo:z_hi] x this rank's angle block | None if empty)]``."""
@@ -249,54 +282,6 @@ class ShardedOperator:
         if comm is not None:
             compute.wait_stream(comm)
 
-    # ------------------------------------------------- row-blocked forward --
-    def _fp_row_blocks(self):
-        """Plan of the overlapped forward projection: ``(gather order, [(ready, v0, v1, z0, z1, operator)])``.
-
-        A block of detector rows only sees the slices its rays can reach (for a cone beam: a z range about as tall
-        as the block), so its forward projection can start as soon as the z-chunks covering that range have been
-        all-gathered - the remaining chunks arrive behind its kernels.  The row blocks and their slice ranges are the
-        ones the library plans for host arrays (``tsp_projector_host_plan``, bounds checked in
-        tests/test_host_plan.py); chunks are gathered from the outside in, because the outermost rows need the
-        fewest slices.  ``ready`` = index in the gather order of the last chunk a block waits for.  ``None`` when
-        the rank-local operator is not the library's or the problem is too small to be cut."""
-        if self._fp_blocks is not False:
-            return self._fp_blocks
-        self._fp_blocks = None
-        proj = getattr(self.local, "astra_projector", None)
-        if self.world == 1 or self.chunks < 2 or proj is None or not hasattr(proj, "host_plan") or os.environ.get("TSP_SHARD_NO_FP_BLOCKS"):
-            return None
-        from . import _backend
-
-        plan = proj.host_plan(_backend.FP)
-        if len(plan) < 2:
-            return None
-        order = []
-        lo, hi = 0, self.chunks - 1
-        while lo <= hi:                                   # outside in: 0, K-1, 1, K-2, ...
-            order.append(lo)
-            if hi != lo:
-                order.append(hi)
-            lo, hi = lo + 1, hi - 1
-        pos = {c: i for i, c in enumerate(order)}
-        blocks = []
-        for z0, z1, v0, v1 in sorted(plan, key=lambda e: e[2]):
-            need = [c for c in range(self.chunks) if self.chunk_bounds(c)[0] < z1 and self.chunk_bounds(c)[1] > z0]
-            ready = max(pos[c] for c in need) if need else 0
-            if blocks and blocks[-1][0] == ready and blocks[-1][2] == v0:   # merge neighbours that start together
-                r, a, _, za, zb = blocks[-1]
-                blocks[-1] = (r, a, v1, min(za, z0), max(zb, z1))
-            else:
-                blocks.append((ready, v0, v1, z0, z1))
-        if len(blocks) < 2 or min(b[0] for b in blocks) == len(order) - 1:
-            return None                                   # nothing can start early
-        out = []
-        for ready, v0, v1, z0, z1 in sorted(blocks):
-            op = self._make_local(self.volume_geometry[z0:z1], self.local_pg[:, v0:v1, :])
-            out.append((ready, v0, v1, z0, z1, op))
-        self._fp_blocks = (order, out)
-        return self._fp_blocks
-
     # ------------------------------------------------------------ operator --
     def __call__(self, x_slab, out=None):
         """``y_block = A[angle block] (all_gather(x_slab))``."""
@@ -308,28 +293,29 @@ class ShardedOperator:
         x_slab = x_slab.contiguous()
         if out is None:
             out = torch.empty(self.proj_shape, dtype=torch.float32, device=x_slab.device)
+        # (A forward projection cut into detector row blocks that start behind the z-chunks they need, so that the
+        # rest of the all-gather hides behind their kernels, was built and measured in round 2: the blocks' extra
+        # launches, wave tails and per-block transposes cost more than the all-gather they hide - 24.5 vs 22.5 ms at
+        # N = 2, 6.56 vs 6.29 ms at N = 8, cfg 3 - and it was dropped.)
+        full_t = self._transposed_volume(x_slab) if (out.is_contiguous() and out.dtype == torch.float32) else None
         compute, comm = self._streams(x_slab)
-        plan = self._fp_row_blocks() if (comm is not None and out.is_contiguous()) else None
-        if plan is None:
+        if full_t is None or comm is None:
             for c in range(self.chunks):
                 self._all_gather_chunk(full, x_slab, c)
             self.local(full[: self.vol_shape[0]], out=out)
             return out
-        # chunk-wise all-gather on the communication stream; every row block starts behind the chunks it needs
-        order, blocks = plan
-        comm.wait_stream(compute)                          # earlier readers of `full`, the producer of x_slab
-        arrived = []
-        with torch.cuda.stream(comm):
-            for c in order:
+        # x-marching ranks: gather chunk by chunk on the communication stream and transpose every chunk as it lands,
+        # behind the all-gather of the next one; the forward projection then reads the finished copy
+        comm.wait_stream(compute)                          # earlier readers of the replicated buffers, producer of x_slab
+        for c in range(self.chunks):
+            with torch.cuda.stream(comm):
                 self._all_gather_chunk(full, x_slab, c)
                 ev = torch.cuda.Event()
                 ev.record(comm)
-                arrived.append(ev)
-        for ready, v0, v1, z0, z1, op in blocks:
-            compute.wait_event(arrived[ready])
-            op(full[z0:z1], out=out[v0:v1])
-        compute.wait_event(arrived[-1])                    # `full` is complete for whoever reads it next
+            compute.wait_event(ev)
+            self._transpose_chunk(full, full_t, c)
         x_slab.record_stream(comm)
+        self._fp_local(full, full_t, out)
         return out
 
     def _bp(self, y_block, out=None):
@@ -347,10 +333,13 @@ class ShardedOperator:
         return out
 
     # ------------------------------------------------------ fused residual --
-    def residual(self, x_full, y, R, out):
+    def residual(self, x_full, y, R, out, x_full_t=None):
         """``out = R * (A[angle block] x_full - y)`` for a replicated volume: in the projector's
-        store when the rank-local operator is the library's (CUDA), else the explicit three passes."""
+        store when the rank-local operator is the library's (CUDA), else the explicit three passes.
+        ``x_full_t``: the caller-maintained transposed copy of ``x_full`` (see :meth:`_transposed_volume`)."""
         proj = getattr(self.local, "astra_projector", None)
+        if x_full_t is not None and all(t.dtype == torch.float32 and t.is_contiguous() for t in (y, R, out)):
+            return self._fp_local(x_full, x_full_t, out, y, R)
         if (proj is not None and x_full.is_cuda and hasattr(proj, "project_fused") and not self.local.additive
                 and all(t.dtype == torch.float32 and t.is_contiguous() for t in (x_full, y, R, out))):
             from . import _backend
@@ -437,8 +426,11 @@ def _sirt_overlapped(A, y, R, C, x_cur, y_tmp, num_iterations):
     if not x_cur.is_contiguous():
         raise ValueError("x must be contiguous")
     x_full = A._full_volume(y)
+    x_full_t = A._transposed_volume(y)                     # None unless this rank's angles march along x
     for c in range(A.chunks):
         A._all_gather_chunk(x_full, x_cur, c)
+        if x_full_t is not None:
+            A._transpose_chunk(x_full, x_full_t, c)
     partial = A._partial_volume(y)
     piece = torch.empty((A.piece_nz,) + tuple(A.slab_shape[1:]), dtype=torch.float32, device=y.device)
     y = y.contiguous()
@@ -447,8 +439,10 @@ def _sirt_overlapped(A, y, R, C, x_cur, y_tmp, num_iterations):
         A._reduce_scatter_chunk(piece, partial, c)
         A._piece_view(x_cur, c).addcmul_(A._piece_view(C, c), piece, value=-1.0)   # x -= C * sum_r A_r^T y_tmp
         A._all_gather_chunk(x_full, x_cur, c)
+        if x_full_t is not None:                           # on the communication stream, behind chunk c + 1's kernel
+            A._transpose_chunk(x_full, x_full_t, c)
 
     for _ in range(num_iterations):
-        A.residual(x_full[: A.vol_shape[0]], y, R, y_tmp)
+        A.residual(x_full[: A.vol_shape[0]], y, R, y_tmp, x_full_t)
         A._bp_chunks(y_tmp, partial, after_chunk)
     return x_cur
