@@ -1,0 +1,4 @@
+set -x
+TSP_BP_ZPT=64 timeout 120 python scratch/prof_step.py 512 720 2 2>&1 | tail -2
+timeout 120 python scratch/prof_step.py 512 720 2 2>&1 | tail -2
+TSP_BP_ZPT=64 timeout 300 python -m pytest tests/test_gpu_kernels.py tests/test_gpu_variants.py -m gpu -q -x -k "bp or BP or matches" 2>&1 | tail -3

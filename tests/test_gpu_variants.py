@@ -48,7 +48,7 @@ FP_VARIANTS = [
     {"TSP_FP_STAGES": 2},
 ]
 BP_VARIANTS = [{}, {"TSP_BP_NO_TMA": 1}, {"TSP_BP_ZPT": 1}, {"TSP_BP_ZPT": 4}, {"TSP_BP_ZPT": 8}, {"TSP_BP_ZPT": 16},
-               {"TSP_BP_ZPT": 32}]
+               {"TSP_BP_ZPT": 32}, {"TSP_BP_ZPT": 64}, {"TSP_BP_ROWS": 2}]
 
 
 def _ids(v):

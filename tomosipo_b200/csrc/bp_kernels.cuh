@@ -404,6 +404,9 @@ __device__ __forceinline__ void bp_tile_loop_zinv3(uint32_t sbase, float nu, flo
 // formed once (2 taps, one packed lerp per voxel pair) and h(j_i) is selected from the previous
 // voxel's two values: 2 shared-memory taps and 9.5 instructions per voxel instead of 3 / 11.
 // The loop is pitch-agnostic (the row pitch is a register), so one copy serves both TMA variants.
+// (A variant with the row coordinate as a 32-bit fixed-point phase - carry = "advance one row", weight = I2FP(phase) -
+// moves 5 of the 11 FMA-pipe instructions per voxel pair to the integer pipe but needs 22 instead of 19 instructions:
+// 51.5 vs 47.7 ms, r02 GPU call 17.  The kernel is bound by instruction issue, not by either math pipe.)
 template <bool CONE, int ZPT>
 __device__ __forceinline__ void bp_tile_loop_rows(uint32_t sbase, uint32_t pitch4, float nu, float nv, float dn, float sv,
                                                   float wpar, uint32_t magic_off, float (&acc)[ZPT])
@@ -609,6 +612,10 @@ constexpr int BP_TMA_HELPERS = 2;
 constexpr int BP_TMA_HELPERS = 1;
 #endif
 constexpr int BP_TMA_THREADS = BP_TMA_CONSUMERS + 32 * BP_TMA_HELPERS;
+// "tall" variant (ZPT = 64): a 32 x 16 x 64 tile, one CTA of 16 consumer warps per SM; the per-angle work of a thread
+// (map, reciprocal, hand-off: ~67 instructions) is spread over twice the voxels
+__host__ __device__ constexpr int bp_tma_ty(int zpt) { return zpt >= 64 ? 16 : BP_TY; }
+__host__ __device__ constexpr int bp_tma_threads(int zpt) { return BP_TX * bp_tma_ty(zpt) + 32 * BP_TMA_HELPERS; }
 #ifndef BP_TMA_STAGES_Z32
 #define BP_TMA_STAGES_Z32 4  // ring depth at 32 voxels per thread (tuning: -DBP_TMA_STAGES_Z32=n)
 #endif
@@ -620,7 +627,7 @@ __host__ __device__ constexpr size_t bp_tma_smem_bytes(int zpt)
 {
     return bp_tma_stages(zpt) * (bp_tma_stage_bytes(zpt) + sizeof(BPLocal) + 16) + 128 + 16 + 2 * 20 * 33 * 4;
 }
-__host__ __device__ constexpr int bp_tma_min_ctas(int zpt) { return zpt >= 32 ? 2 : 3; }
+__host__ __device__ constexpr int bp_tma_min_ctas(int zpt) { return zpt >= 64 ? 1 : (zpt >= 32 ? 2 : 3); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
@@ -663,7 +670,7 @@ __device__ __forceinline__ void tma_load_box_3d(uint32_t dst, const void *tmap, 
 }
 
 template <bool CONE, int ZPT>
-__global__ void __launch_bounds__(BP_TMA_THREADS, bp_tma_min_ctas(ZPT))
+__global__ void __launch_bounds__(bp_tma_threads(ZPT), bp_tma_min_ctas(ZPT))
 bp_tma_kernel(const BPArgs P, const __grid_constant__ TensorMapPair tmaps)  // m[0]: pitch 68 boxes, m[1]: pitch 60
 {
     const TensorMapBlob *tmap = tmaps.m;
@@ -692,9 +699,10 @@ bp_tma_kernel(const BPArgs P, const __grid_constant__ TensorMapPair tmaps)  // m
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int x0 = blockIdx.x * BP_TX, y0 = blockIdx.y * BP_TY, z0 = blockIdx.z * ZPT;
+    constexpr int TY = bp_tma_ty(ZPT);
+    const int x0 = blockIdx.x * BP_TX, y0 = blockIdx.y * TY, z0 = blockIdx.z * ZPT;
     // z is not clipped to the volume: every thread walks its whole z run (only the store is guarded)
-    const int x1 = min(x0 + BP_TX, P.nx) - 1, y1 = min(y0 + BP_TY, P.ny) - 1, z1 = z0 + ZPT - 1;
+    const int x1 = min(x0 + BP_TX, P.nx) - 1, y1 = min(y0 + TY, P.ny) - 1, z1 = z0 + ZPT - 1;
     const double xc = 0.5 * (x0 + x1) + 0.5 - 0.5 * P.nx, hx = 0.5 * (x1 - x0);
     const double yc = 0.5 * (y0 + y1) + 0.5 - 0.5 * P.ny, hy = 0.5 * (y1 - y0);
     const double zc = 0.5 * (z0 + z1) + 0.5 - 0.5 * P.nz, hz = 0.5 * (z1 - z0);
@@ -702,7 +710,7 @@ bp_tma_kernel(const BPArgs P, const __grid_constant__ TensorMapPair tmaps)  // m
     if (tid == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(full + 8u * s, 1);                       // the producer's arrive(+expect_tx)
-            mbar_init(empty + 8u * s, BP_TMA_CONSUMERS / 32);  // one arrival per consumer warp
+            mbar_init(empty + 8u * s, TY);                     // one arrival per consumer warp
         }
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(ready), "r"(0u) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -710,7 +718,7 @@ bp_tma_kernel(const BPArgs P, const __grid_constant__ TensorMapPair tmaps)  // m
     __syncthreads();
 
 #ifdef BP_PUBLISHER
-    if (warp == BP_TMA_CONSUMERS / 32 + 1) {
+    if (warp == TY + 1) {
         // ----------------------------------------------------------- publisher
         int s = 0;
         uint32_t parity = 0u;
@@ -722,7 +730,7 @@ bp_tma_kernel(const BPArgs P, const __grid_constant__ TensorMapPair tmaps)  // m
         return;
     }
 #endif
-    if (warp == BP_TMA_CONSUMERS / 32) {
+    if (warp == TY) {
         // ------------------------------------------------------------ producer
         // A pass = 32 angles, one per lane (bp_setup_lane).  The lane's map goes to a transposed scratch table
         // `pend` (word f of angle g at [f * 33 + g]: conflict-free both ways); when angle g's ring stage is free,

@@ -769,8 +769,13 @@ static int bp_zpt_choice(int nx, int ny, int nz)
 {
     if (const char *e = getenv("TSP_BP_ZPT")) {
         const int v = atoi(e);
-        if (v == 1 || v == 4 || v == 8 || v == 16 || v == 24 || v == 32) return v;
+        if (v == 1 || v == 4 || v == 8 || v == 16 || v == 24 || v == 32 || v == 64) return v;
     }
+    // the tall tile (32 x 16 x 64, one CTA per SM): 46.2 vs 47.8 ms at cfg 3 (r02 GPU call 18) - when the volume is
+    // at most 1/8 padding along z and gives every SM at least 12 such CTAs (wave tail <= 4 %; TMA kernel only)
+    if (!getenv("TSP_BP_NO_TALL") && (nz % 64 == 0 || nz % 64 >= 56) &&
+        (long long)((nx + BP_TX - 1) / BP_TX) * ((ny + 15) / 16) * ((nz + 63) / 64) >= 12LL * 148)
+        return 64;
     // longest run that (a) is not mostly padding and (b) still leaves >= 4 CTAs per SM to balance
     const int cand[5] = {32, 16, 8, 4, 1};
     const long long tiles_xy = (long long)((nx + BP_TX - 1) / BP_TX) * ((ny + BP_TY - 1) / BP_TY);
@@ -880,7 +885,7 @@ static int launch_bp_tma_one(dim3 grid, cudaStream_t stream, const BPArgs &P, co
         CUDA_TRY(cudaFuncSetAttribute(bp_tma_kernel<CONE, ZPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured[dev] = true;
     }
-    bp_tma_kernel<CONE, ZPT><<<grid, BP_TMA_THREADS, smem, stream>>>(P, tmap);
+    bp_tma_kernel<CONE, ZPT><<<grid, bp_tma_threads(ZPT), smem, stream>>>(P, tmap);
     return TSP_OK;
 }
 
@@ -898,6 +903,7 @@ static int launch_bp_tma_variant(bool cone, int zpt, dim3 grid, cudaStream_t str
         TSP_BP_CASE(16)
         TSP_BP_CASE(24)
         TSP_BP_CASE(32)
+        TSP_BP_CASE(64)
     }
 #undef TSP_BP_CASE
     return fail(TSP_ERR_INVALID, "unsupported z run %d", zpt);
@@ -952,15 +958,17 @@ static int launch_bp(tsp_projector *pr, DeviceState *st, float *vol, const float
         if (cone) bp_supersample_kernel<true><<<grid, block, 0, stream>>>(P);
         else bp_supersample_kernel<false><<<grid, block, 0, stream>>>(P);
     } else {
-        const int zpt = bp_zpt_choice(g.nx, g.ny, g.nz);
-        const int gz = (g.nz + zpt - 1) / zpt;
-        const int gy = (g.ny + BP_TY - 1) / BP_TY;
-        if (gz > 65535 || gy > 65535) return fail(TSP_ERR_INVALID, "volume too large for the BP grid");
-        dim3 grid((g.nx + BP_TX - 1) / BP_TX, gy, gz), block(BP_TX, BP_TY);
+        int zpt = bp_zpt_choice(g.nx, g.ny, g.nz);
         TensorMapPair tmap;
         const bool use_tma = !getenv("TSP_BP_NO_TMA") &&
                              make_proj_tensor_map(proj, g.det_cols, g.n_angles, g.det_rows, BP_TMA_PITCH, bp_wv(zpt), &tmap.m[0]) &&
                              make_proj_tensor_map(proj, g.det_cols, g.n_angles, g.det_rows, BP_TMA_PITCH_B, bp_wv(zpt), &tmap.m[1]);
+        if (!use_tma && zpt > 32) zpt = 32;  // the tall tile exists for the TMA kernel only
+        const int ty = use_tma ? bp_tma_ty(zpt) : BP_TY;
+        const int gz = (g.nz + zpt - 1) / zpt;
+        const int gy = (g.ny + ty - 1) / ty;
+        if (gz > 65535 || gy > 65535) return fail(TSP_ERR_INVALID, "volume too large for the BP grid");
+        dim3 grid((g.nx + BP_TX - 1) / BP_TX, gy, gz), block(BP_TX, BP_TY);
         P.magic_off = 0u - 4u * BP_MAGIC_BITS * (uint32_t)((use_tma ? BP_TMA_PITCH : BP_PITCH) + 1);
         P.magic_off_b = 0u - 4u * BP_MAGIC_BITS * (uint32_t)(BP_TMA_PITCH_B + 1);
         if (use_tma) {
