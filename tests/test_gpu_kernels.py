@@ -116,19 +116,41 @@ def test_additive_mode():
     assert rel_l2(x2, ref) <= TOL
 
 
+@pytest.mark.parametrize("direct", [False, True], ids=["staged", "direct"])
 @pytest.mark.parametrize("kind", ["cone", "par_aniso"])
-def test_supersampling(kind):
+def test_supersampling(kind, direct):
+    """VoxelSuperSampling / DetectorSuperSampling (reference tomosipo/astra.py:84-97, doc/topics/operator.rst:69-86):
+    through the staged kernels on the refined geometry + pooling (default), and the direct kernels (TSP_SS_DIRECT=1);
+    SET, ADD, and factors 2 and 3."""
+    import os
+
     case = [c for c in cases() if c[0] == kind][0]
     name, k, vs, win, ds, vec = case
     vs = tuple(max(1, s // 2) for s in vs)
-    P, Q = make(k, vs, win, ds, vec, vss=2, dss=2)
-    rng = np.random.default_rng(0)
-    x = rng.random(vs).astype(np.float32)
-    y = rng.random(Q.proj_shape).astype(np.float32)
-    _, yy = _run(P, 0, x, np.zeros(Q.proj_shape, np.float32))
-    xx, _ = _run(P, 1, np.zeros(vs, np.float32), y)
-    assert rel_l2(yy, Q.fp(x.astype(np.float64))) <= TOL
-    assert rel_l2(xx, Q.bp(y.astype(np.float64))) <= TOL
+    old = os.environ.pop("TSP_SS_DIRECT", None)
+    if direct:
+        os.environ["TSP_SS_DIRECT"] = "1"
+    try:
+        for vss, dss in ((2, 2), (3, 1), (1, 3)):
+            P, Q = make(k, vs, win, ds, vec, vss=vss, dss=dss)
+            rng = np.random.default_rng(0)
+            x = rng.random(vs).astype(np.float32)
+            y = rng.random(Q.proj_shape).astype(np.float32)
+            _, yy = _run(P, 0, x, np.zeros(Q.proj_shape, np.float32))
+            xx, _ = _run(P, 1, np.zeros(vs, np.float32), y)
+            assert rel_l2(yy, Q.fp(x.astype(np.float64))) <= TOL
+            assert rel_l2(xx, Q.bp(y.astype(np.float64))) <= TOL
+            if (vss, dss) == (2, 2):
+                _, y2 = _run(P, 0, x, y.copy(), additive=True)
+                x2, _ = _run(P, 1, x.copy(), y, additive=True)
+                assert rel_l2(y2, Q.fp(x.astype(np.float64)) + y) <= TOL
+                assert rel_l2(x2, Q.bp(y.astype(np.float64)) + x) <= TOL
+                if not direct and kind == "cone":
+                    assert P.info().fp_uses_tma == 1 and P.info().bp_uses_tma == 1
+    finally:
+        os.environ.pop("TSP_SS_DIRECT", None)
+        if old is not None:
+            os.environ["TSP_SS_DIRECT"] = old
 
 
 def test_host_memory_path():

@@ -866,4 +866,24 @@ __global__ void __launch_bounds__(256) bp_supersample_kernel(const BPArgs P)
     bp_store_one(P, ((size_t)z * P.ny + y) * P.nx + x, acc);
 }
 
+// Voxel supersampling through the staged kernels: vol[z][y][x] = sum of the d^3 voxels of a d-times finer grid (each
+// fine voxel already carries its own, d^3 times smaller, voxel volume, so the sum is voxel volume x the mean over the
+// sub-voxel centres).  Coarse slices z0 .. z0 + nzs are in `fine`, [nzs * d][ny * d][nx * d]; stored with
+// bp_store_one (SET, ADD, fused SIRT update).
+__global__ void __launch_bounds__(256) bp_pool_kernel(const BPArgs P, const float *__restrict__ fine, int d, int z0, int nzs)
+{
+    const int x = blockIdx.x * 32 + threadIdx.x;
+    const int y = blockIdx.y * 8 + threadIdx.y;
+    const int z = blockIdx.z;
+    if (x >= P.nx || y >= P.ny || z >= nzs) return;
+    const size_t fx = (size_t)P.nx * d, fplane = fx * P.ny * d;
+    float sum = 0.0f;
+    for (int sz = 0; sz < d; ++sz)
+        for (int sy = 0; sy < d; ++sy) {
+            const float *src = fine + (size_t)(z * d + sz) * fplane + (size_t)(y * d + sy) * fx + (size_t)x * d;
+            for (int sx = 0; sx < d; ++sx) sum += __ldg(src + sx);
+        }
+    bp_store_one(P, ((size_t)(z0 + z) * P.ny + y) * P.nx + x, sum);
+}
+
 }  // namespace tsp

@@ -380,4 +380,22 @@ __global__ void __launch_bounds__(256) transpose_xy_kernel(const float *__restri
     }
 }
 
+// Detector supersampling through the staged kernels: proj[v][a][u] = mean of the d x d pixels of a d-times finer
+// detector (rows v0 .. v0 + nv of the coarse detector are in `fine`, [nv * d][A][U * d]); stored with fp_store, so SET,
+// ADD and the fused SIRT residual behave as in the direct kernels.
+__global__ void __launch_bounds__(256) fp_pool_kernel(const FPArgs P, const float *__restrict__ fine, int d, int v0, int nv)
+{
+    const int u = blockIdx.x * 32 + threadIdx.x;
+    const int a = blockIdx.y * 8 + threadIdx.y;
+    const int v = blockIdx.z;
+    if (u >= P.det_u || a >= P.n_angles || v >= nv) return;
+    const size_t fu = (size_t)P.det_u * d, frow = fu * P.n_angles;
+    float sum = 0.0f;
+    for (int sv = 0; sv < d; ++sv) {
+        const float *src = fine + ((size_t)(v * d + sv)) * frow + (size_t)a * fu + (size_t)u * d;
+        for (int su = 0; su < d; ++su) sum += __ldg(src + su);
+    }
+    fp_store(P, ((size_t)(v0 + v) * P.n_angles + a) * P.det_u + u, sum / (float)(d * d));
+}
+
 }  // namespace tsp

@@ -97,6 +97,10 @@ struct tsp_projector {
     };
     std::vector<HostChunk> host_bp, host_fp;
     bool host_planned = false;
+    // Supersampling through the staged kernels: sub-projectors on the refined geometry (z-slabs of the fine volume for
+    // VoxelSuperSampling, row blocks of the fine detector for DetectorSuperSampling); z0 / z1 / v0 / v1 are COARSE indices.
+    std::vector<HostChunk> ss_bp, ss_fp;
+    bool ss_planned = false;
     std::atomic<int> host_pipelined{0};  // last host-array call ran the chunked pipeline
     std::atomic<int> host_ring{0};       // ... out of the bounded ring of chunk buffers (device memory budget exceeded)
     std::atomic<int> host_devices{0};    // ... on this many devices

@@ -389,8 +389,12 @@ extern "C" void tsp_projector_destroy(tsp_projector *pr)
     if (!pr) return;
     for (auto &c : pr->host_bp) tsp_projector_destroy(c.sub);
     for (auto &c : pr->host_fp) tsp_projector_destroy(c.sub);
+    for (auto &c : pr->ss_bp) tsp_projector_destroy(c.sub);
+    for (auto &c : pr->ss_fp) tsp_projector_destroy(c.sub);
     pr->host_bp.clear();
     pr->host_fp.clear();
+    pr->ss_bp.clear();
+    pr->ss_fp.clear();
     if (!pr->dev.empty()) free_device_state(pr);
     delete pr;
 }
@@ -540,6 +544,12 @@ struct PoolScratch {
 static bool make_tensor_map_3d(const float *base, const uint64_t dims[3], const uint64_t stride_bytes[2],
                                const uint32_t box[3], TensorMapBlob *out);
 
+// supersampling through the staged kernels (defined with the sub-projector machinery further down)
+static int launch_fp_supersampled(tsp_projector *pr, DeviceState *st, const float *vol, float *proj, int additive, cudaStream_t stream,
+                                  const float *epi_sub, const float *epi_mul);
+static int launch_bp_supersampled(tsp_projector *pr, DeviceState *st, float *vol, const float *proj, int additive, cudaStream_t stream,
+                                  const float *epi_mul);
+
 template <bool CONE, bool COLS, int R, int SPS>
 static int launch_fp_tma_one(dim3 grid, size_t smem, cudaStream_t stream, const FPTmaArgs &A, const TensorMapPair &tmap)
 {
@@ -575,6 +585,10 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
         return TSP_OK;
     }
 
+    if (g.detector_supersampling > 1 && !thin && !getenv("TSP_SS_DIRECT")) {
+        const int rc = launch_fp_supersampled(pr, st, vol, proj, additive, stream, epi_sub, epi_mul);
+        if (rc != 1) return rc;  // 1: not applicable, take the direct kernels
+    }
     bool need_t = false;
     for (const FPGroup &grp : pr->groups) need_t |= grp.transposed;
     // the transpose grid covers nz * batch planes: a batch too tall for it goes item by item
@@ -953,6 +967,10 @@ static int launch_bp(tsp_projector *pr, DeviceState *st, float *vol, const float
         else TSP_THIN_BP(false);
 #undef TSP_THIN_BP
     } else if (g.voxel_supersampling > 1) {
+        if (!getenv("TSP_SS_DIRECT")) {
+            const int rc = launch_bp_supersampled(pr, st, vol, proj, additive, stream, epi_mul);
+            if (rc != 1) return rc;  // 1: not applicable, take the direct kernel
+        }
         if (g.nz > 65535) return fail(TSP_ERR_INVALID, "voxel supersampling supports nz <= 65535");
         dim3 grid((g.nx + 31) / 32, (g.ny + 7) / 8, g.nz), block(32, 8);
         if (cone) bp_supersample_kernel<true><<<grid, block, 0, stream>>>(P);
@@ -1030,6 +1048,145 @@ static tsp_projector *make_sub_projector(const tsp_projector *pr, int z0, int z1
     tsp_projector *sub = nullptr;
     if (create_projector_internal(&g, pr->march_axis.data(), &sub) != TSP_OK) return nullptr;
     return sub;
+}
+
+// ---- supersampling through the staged kernels -----------------------------------------------------------------------
+// VoxelSuperSampling d: the mean over d^3 sub-voxel centres (reference doc/topics/operator.rst:77-81) is the
+// backprojection onto a d-times finer grid, summed over each coarse voxel.  DetectorSuperSampling d: the mean over
+// d^2 sub-rays (:83-86) is the forward projection onto a d-times finer detector, averaged over each coarse pixel.
+// Both therefore run the ordinary TMA kernels on a refined geometry, slab by slab / row block by row block through a
+// bounded scratch buffer, followed by a pooling kernel (the direct kernels - one thread per voxel with fp64
+// sub-voxel arithmetic, plain-load FP - remain as the fall-back and as the cross-check, TSP_SS_DIRECT=1).
+static tsp_projector *make_fine_projector(const tsp_projector *pr, int vox_d, int det_d)
+{
+    tsp_geometry g = pr->g;
+    std::vector<double> vec = pr->vectors;
+    g.nx *= vox_d; g.ny *= vox_d; g.nz *= vox_d;
+    g.det_rows *= det_d; g.det_cols *= det_d;
+    for (int a = 0; a < g.n_angles; ++a)
+        for (int i = 0; i < 6; ++i) vec[12 * (size_t)a + 6 + i] /= det_d;  // pixel vectors; the detector centre stays
+    g.voxel_supersampling = g.detector_supersampling = 1;
+    g.vectors = vec.data();
+    tsp_projector *fine = nullptr;
+    if (create_projector_internal(&g, pr->march_axis.data(), &fine) != TSP_OK) return nullptr;
+    return fine;
+}
+
+static bool plan_supersampling(tsp_projector *pr)
+{
+    std::lock_guard<std::mutex> lock(pr->mu);
+    if (pr->ss_planned) return !pr->ss_bp.empty() || !pr->ss_fp.empty();
+    pr->ss_planned = true;
+    const tsp_geometry &g = pr->g;
+    const size_t budget = (size_t)256 << 20;  // scratch bytes per sub-problem
+    if (g.voxel_supersampling > 1) {
+        const int d = g.voxel_supersampling;
+        tsp_projector *fine = make_fine_projector(pr, d, 1);
+        if (fine) {
+            const size_t fine_slice = (size_t)g.nx * d * g.ny * d * d * sizeof(float);  // bytes of one COARSE slice
+            int s = (int)std::max<size_t>(1, std::min<size_t>(32, budget / std::max<size_t>(1, fine_slice)));
+            for (int z0 = 0; z0 < g.nz; z0 += s) {
+                tsp_projector::HostChunk c;
+                c.z0 = z0; c.z1 = std::min(g.nz, z0 + s); c.v0 = 0; c.v1 = g.det_rows;
+                c.sub = make_sub_projector(fine, c.z0 * d, c.z1 * d, 0, g.det_rows);
+                if (!c.sub) break;
+                pr->ss_bp.push_back(c);
+            }
+            tsp_projector_destroy(fine);
+            if (pr->ss_bp.empty() || pr->ss_bp.back().z1 != g.nz) {
+                for (auto &c : pr->ss_bp) tsp_projector_destroy(c.sub);
+                pr->ss_bp.clear();
+            }
+        }
+    }
+    if (g.detector_supersampling > 1) {
+        const int d = g.detector_supersampling;
+        tsp_projector *fine = make_fine_projector(pr, 1, d);
+        if (fine) {
+            const size_t fine_row = (size_t)g.n_angles * g.det_cols * d * d * sizeof(float);  // bytes of one COARSE row
+            int r = (int)std::max<size_t>(1, std::min<size_t>(32, budget / std::max<size_t>(1, fine_row)));
+            for (int v0 = 0; v0 < g.det_rows; v0 += r) {
+                tsp_projector::HostChunk c;
+                c.v0 = v0; c.v1 = std::min(g.det_rows, v0 + r); c.z0 = 0; c.z1 = g.nz;
+                c.sub = make_sub_projector(fine, 0, g.nz, c.v0 * d, c.v1 * d);
+                if (!c.sub) break;
+                pr->ss_fp.push_back(c);
+            }
+            tsp_projector_destroy(fine);
+            if (pr->ss_fp.empty() || pr->ss_fp.back().v1 != g.det_rows) {
+                for (auto &c : pr->ss_fp) tsp_projector_destroy(c.sub);
+                pr->ss_fp.clear();
+            }
+        }
+    }
+    return !pr->ss_bp.empty() || !pr->ss_fp.empty();
+}
+
+static int launch_bp_supersampled(tsp_projector *pr, DeviceState *st, float *vol, const float *proj, int additive, cudaStream_t stream,
+                                  const float *epi_mul)
+{
+    plan_supersampling(pr);
+    if (pr->ss_bp.empty()) return 1;
+    const tsp_geometry &g = pr->g;
+    const int d = g.voxel_supersampling;
+    int device = 0;
+    CUDA_TRY(cudaGetDevice(&device));
+    size_t max_elems = 0;
+    for (const auto &c : pr->ss_bp) max_elems = std::max(max_elems, (size_t)(c.z1 - c.z0) * d * g.ny * d * g.nx * d);
+    PoolScratch scratch;
+    scratch.stream = stream;
+    pool_keep_at_least(st, st->pool_keep_base + max_elems * sizeof(float));
+    CUDA_TRY(pool_alloc(st, &scratch.p, max_elems * sizeof(float), stream));
+    BPArgs P;
+    memset(&P, 0, sizeof P);
+    P.vol = vol; P.nx = g.nx; P.ny = g.ny; P.nz = g.nz;
+    P.additive = additive; P.epi_mul = epi_mul;
+    for (const auto &c : pr->ss_bp) {
+        DeviceState *sst = nullptr;
+        if (int rc = get_device_state(c.sub, device, &sst)) return rc;
+        const int64_t l0 = c.sub->launches;
+        if (int rc = launch_bp(c.sub, sst, (float *)scratch.p, proj, 0, stream)) return rc;  // the same scratch: stream order
+        pr->launches += c.sub->launches - l0 + 1;
+        pr->bp_uses_tma = c.sub->bp_uses_tma.load();
+        dim3 grid((g.nx + 31) / 32, (g.ny + 7) / 8, c.z1 - c.z0), block(32, 8);
+        bp_pool_kernel<<<grid, block, 0, stream>>>(P, (const float *)scratch.p, d, c.z0, c.z1 - c.z0);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return TSP_OK;
+}
+
+static int launch_fp_supersampled(tsp_projector *pr, DeviceState *st, const float *vol, float *proj, int additive, cudaStream_t stream,
+                                  const float *epi_sub, const float *epi_mul)
+{
+    plan_supersampling(pr);
+    if (pr->ss_fp.empty()) return 1;
+    const tsp_geometry &g = pr->g;
+    const int d = g.detector_supersampling;
+    int device = 0;
+    CUDA_TRY(cudaGetDevice(&device));
+    size_t max_elems = 0;
+    for (const auto &c : pr->ss_fp) max_elems = std::max(max_elems, (size_t)(c.v1 - c.v0) * d * g.n_angles * g.det_cols * d);
+    PoolScratch scratch;
+    scratch.stream = stream;
+    pool_keep_at_least(st, st->pool_keep_base + max_elems * sizeof(float));
+    CUDA_TRY(pool_alloc(st, &scratch.p, max_elems * sizeof(float), stream));
+    FPArgs P;
+    memset(&P, 0, sizeof P);
+    P.proj = proj; P.det_u = g.det_cols; P.det_v = g.det_rows; P.n_angles = g.n_angles;
+    P.additive = additive; P.epi_sub = epi_sub; P.epi_mul = epi_mul;
+    for (const auto &c : pr->ss_fp) {
+        DeviceState *sst = nullptr;
+        if (int rc = get_device_state(c.sub, device, &sst)) return rc;
+        const int64_t l0 = c.sub->launches;
+        if (int rc = launch_fp(c.sub, sst, vol, (float *)scratch.p, 0, stream)) return rc;
+        pr->launches += c.sub->launches - l0 + 1;
+        pr->fp_uses_tma = c.sub->fp_uses_tma.load(); pr->fp_uses_transpose = c.sub->fp_uses_transpose.load();
+        dim3 grid((g.det_cols + 31) / 32, (g.n_angles + 7) / 8, c.v1 - c.v0), block(32, 8);
+        if ((g.n_angles + 7) / 8 > 65535 || c.v1 - c.v0 > 65535) return fail(TSP_ERR_INVALID, "too many angles for the pooling grid");
+        fp_pool_kernel<<<grid, block, 0, stream>>>(P, (const float *)scratch.p, d, c.v0, c.v1 - c.v0);
+    }
+    CUDA_TRY(cudaGetLastError());
+    return TSP_OK;
 }
 
 // detector rows [v0, v1) that voxels of the slab z0 <= z < z1 can touch (bilinear taps included)
