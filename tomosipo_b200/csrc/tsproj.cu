@@ -700,8 +700,13 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
                 if (!bw[0]) bw[0] = bw[1] ? bw[1] : need_w;
                 if (!bw[1]) bw[1] = bw[0];
                 if (bw[0] > 256 || bw[1] > 256) bw[0] = bw[1] = need_w;
-                const size_t stage = ((size_t)std::max(bw[0], bw[1]) * box_h * sps * 4 + 127) / 128 * 128 + 24;
+                size_t stage = ((size_t)std::max(bw[0], bw[1]) * box_h * sps * 4 + 127) / 128 * 128 + 24;
                 if (sps == 1 || 3 * stage + 160 <= budget) break;
+                // tall boxes (row blocks far from the mid-plane: the host pipeline's sub-projectors): one pitch for both
+                // variants - a few more bank conflicts for half of the CTAs - rather than one slice per stage
+                bw[0] = bw[1] = std::min(bw[0], bw[1]);
+                stage = ((size_t)bw[0] * box_h * sps * 4 + 127) / 128 * 128 + 24;
+                if (3 * stage + 160 <= budget) break;
             }
             TensorMapPair slot;
             bool ok = box_h <= 256;
