@@ -13,12 +13,18 @@ Contract: ``python bench.py --gpus N --steps K --warmup W`` prints ONE JSON line
 * roofline   for the dominant kernel: algorithmic bytes 4*(vol + proj) per
              launch over its measured duration, against the measured HBM peak;
              `traffic` = DRAM bytes per launch from the committed ncu capture
-             (profiles/r01_traffic.json); `interp` adds the in-SM interpolation
-             view (updates/clk/SM) that actually bounds these kernels.
+             (profiles/r02_traffic.json, `traffic_source` says so); `interp` adds
+             the in-SM interpolation view (updates/clk/SM) that actually bounds
+             these kernels.
 * sirt       SIRT iterations/s on the same problem (BASELINE.json metric, second
              half): fused tsp_sirt at N = 1, sharded loop at N > 1.
+* cfg4_sirt  SIRT ms / iteration at BASELINE configs[3] (1024^3 x 1440), the
+             configuration the north_star's scaling target is written on.
+* sharded_parity_rel_l2 (N > 1): the NCCL-sharded operator against the
+             single-GPU operator on a 128^3 problem, max over ranks.
 * cpu_baseline / --impl reference: the CPU restatement (oracle/, fp32,
-             OpenMP, all host cores) on a bounded sample of the same workload.
+             OpenMP, all host cores) on the headline volume and detector over a
+             sample of the 720 angles (cost is linear in angles).
              ASTRA -- the reference's engine -- has no CPU 3-D projector and is
              not installable here, so the port is the CPU arm.
 """
@@ -524,9 +530,10 @@ def run_ours(args):
         "fp_updates_per_clk_per_sm": upd / (fp_ms * 1e-3) / (sm_mhz * 1e6) / 148,
         "bp_updates_per_clk_per_sm": upd / (bp_ms * 1e-3) / (sm_mhz * 1e6) / 148,
         "ceiling_updates_per_clk_per_sm": 8.9,
-        "ceiling_note": "measured on B200 (scratch/ubench/gather_ceiling.cu, profiles/r01_gather_ceiling.txt): 4 conflict-free "
-                        "LDS.32 taps per update and nothing else = 8.91 updates/clk/SM; with scalar bilinear arithmetic 6.33; "
-                        "the 3-row BP loop (6 taps per voxel pair) 9.52",
+        "ceiling_note": "measured on B200 (scratch/ubench/gather_ceiling.cu, tex_arm.cu; profiles/r02_texture_vs_shared.md): "
+                        "shared memory, 4 conflict-free LDS.32 taps per update and nothing else = 8.91 updates/clk/SM; with scalar "
+                        "bilinear arithmetic 6.33; 3-row BP loop 9.52; texture unit with hardware bilinear (9-bit weights) 4.17, "
+                        "with TLD4 + exact fp32 lerp 2.00",
         "fp_kernel": fp_name, "bp_kernel": bp_name,
     }
     t_dom = traffic.get(dom) if world == 1 and not big else None  # the ncu capture is of cfg 3 on one GPU

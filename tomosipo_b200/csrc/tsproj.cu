@@ -1313,6 +1313,9 @@ static bool plan_host_pipeline(tsp_projector *pr)
     // rows must arrive before any kernel runs) and the row block the FP ends with (its download follows the
     // last kernel) are halved
     std::vector<std::pair<int, int>> zr, vr;
+    // (Graded sizes - 32 / 64 at the two exposed ends of the pipeline, chunks of up to n / 4 in between - were measured
+    // at cfg 3: 1 801 GUPS against 1 892 for these uniform chunks, r02 GPU call 23: the coarse middle chunks pipeline
+    // worse than their fewer launches save.)
     for (int z0 = 0; z0 < g.nz; z0 += cz) zr.push_back({z0, std::min(g.nz, z0 + cz)});
     for (int v0 = 0; v0 < g.det_rows; v0 += cv) vr.push_back({v0, std::min(g.det_rows, v0 + cv)});
     if (!getenv("TSP_HOST_UNIFORM")) {
