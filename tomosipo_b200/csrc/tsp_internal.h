@@ -67,6 +67,8 @@ struct DeviceState {
     cudaStream_t s_in = nullptr, s_out = nullptr;
     // private stream-ordered memory pool of this (projector, device): per-call scratch and host-array staging
     cudaMemPool_t pool = nullptr;
+    bool owns_pool = true;      // false: the pool belongs to the projector this one is a sub-projector of
+    DeviceState *pool_st = nullptr;  // ... and this is that projector's state (its release threshold is the one that counts)
     size_t pool_keep = 0;       // current release threshold
     size_t pool_keep_base = 0;  // the part kept for device-array calls (transposed-volume scratch)
 };
@@ -74,6 +76,7 @@ struct DeviceState {
 }  // namespace tsp
 
 struct tsp_projector {
+    tsp_projector *pool_owner = nullptr;  // sub-projectors allocate from their owner's memory pool
     tsp_geometry g;
     std::vector<double> vectors;
     double sigma[3];

@@ -378,7 +378,7 @@ static void free_device_state(tsp_projector *pr)
         cudaFree(kv.second.bp_angles);
         if (kv.second.s_in) cudaStreamDestroy(kv.second.s_in);
         if (kv.second.s_out) cudaStreamDestroy(kv.second.s_out);
-        if (kv.second.pool) cudaMemPoolDestroy(kv.second.pool);
+        if (kv.second.pool && kv.second.owns_pool) cudaMemPoolDestroy(kv.second.pool);
     }
     cudaSetDevice(cur);
     pr->dev.clear();
@@ -483,16 +483,24 @@ static int get_device_state(tsp_projector *pr, int device, DeviceState **out)
     }
     CUDA_TRY(cudaMalloc(&st.fp_pairs, std::max<size_t>(1, pairs.size()) * sizeof(int)));
     CUDA_TRY(cudaMemcpy(st.fp_pairs, pairs.data(), pairs.size() * sizeof(int), cudaMemcpyHostToDevice));
-    // private pool: caches one transposed-volume scratch between calls, nothing more (see pool_alloc)
-    {
+    // Private pool: caches one transposed-volume scratch between calls, nothing more (see pool_alloc).  Sub-projectors
+    // (host pipeline chunks, supersampling slabs) allocate from the pool of the projector they belong to - one cache
+    // per user-visible projector, not one per chunk.
+    const int ny_pad = (pr->g.ny + 3) / 4 * 4;
+    const uint64_t base = (uint64_t)pr->g.nz * pr->g.nx * ny_pad * sizeof(float);
+    if (pr->pool_owner) {
+        DeviceState *ost = nullptr;
+        if (int rc = get_device_state(pr->pool_owner, device, &ost)) return rc;
+        st.pool = ost->pool;
+        st.owns_pool = false;
+        st.pool_st = ost;
+    } else {
         cudaMemPoolProps props = {};
         props.allocType = cudaMemAllocationTypePinned;
         props.handleTypes = cudaMemHandleTypeNone;
         props.location.type = cudaMemLocationTypeDevice;
         props.location.id = device;
         if (cudaMemPoolCreate(&st.pool, &props) == cudaSuccess) {
-            const int ny_pad = (pr->g.ny + 3) / 4 * 4;
-            const uint64_t base = (uint64_t)pr->g.nz * pr->g.nx * ny_pad * sizeof(float);
             uint64_t keep = base + base / 4 + ((uint64_t)32 << 20);
             if (const char *e = getenv("TSP_POOL_KEEP_MB")) keep = (uint64_t)std::max(0LL, atoll(e)) << 20;
             cudaMemPoolSetAttribute(st.pool, cudaMemPoolAttrReleaseThreshold, &keep);
@@ -524,6 +532,10 @@ static cudaError_t pool_alloc(DeviceState *st, void **p, size_t bytes, cudaStrea
 // call; tsp_projector_destroy gives everything back.
 static void pool_keep_at_least(DeviceState *st, size_t bytes)
 {
+    if (st->pool_st) {  // a sub-projector: its needs come on top of what the owner keeps for itself
+        pool_keep_at_least(st->pool_st, st->pool_st->pool_keep_base + bytes);
+        return;
+    }
     if (!st->pool || bytes <= st->pool_keep) return;
     // the pool reserves whole 2 MB granules per allocation: a threshold equal to the bytes requested is exceeded by the
     // rounding, and the excess block would be unmapped and mapped again on every call (measured: 1.8 instead of 0.65 ms
@@ -791,10 +803,13 @@ static int bp_zpt_choice(int nx, int ny, int nz)
         if (v == 1 || v == 4 || v == 8 || v == 16 || v == 24 || v == 32 || v == 64) return v;
     }
     // the tall tile (32 x 16 x 64, one CTA per SM): 46.2 vs 47.8 ms at cfg 3 (r02 GPU call 18) - when the volume is
-    // at most 1/8 padding along z and gives every SM at least 12 such CTAs (wave tail <= 4 %; TMA kernel only)
-    if (!getenv("TSP_BP_NO_TALL") && (nz % 64 == 0 || nz % 64 >= 56) &&
-        (long long)((nx + BP_TX - 1) / BP_TX) * ((ny + 15) / 16) * ((nz + 63) / 64) >= 12LL * 148)
-        return 64;
+    // at most 1/8 padding along z and gives every SM at least 6 such CTAs with a last wave that is not mostly empty
+    // (TMA kernel only; the z-chunks of the multi-GPU operator qualify, the 64-slice slabs of the host pipeline do not)
+    if (!getenv("TSP_BP_NO_TALL") && (nz % 64 == 0 || nz % 64 >= 56)) {
+        const long long ctas = (long long)((nx + BP_TX - 1) / BP_TX) * ((ny + 15) / 16) * ((nz + 63) / 64);
+        const long long waves = (ctas + 147) / 148;
+        if (ctas >= 6LL * 148 && ctas * 100 >= waves * 148 * 93) return 64;
+    }
     // longest run that (a) is not mostly padding and (b) still leaves >= 4 CTAs per SM to balance
     const int cand[5] = {32, 16, 8, 4, 1};
     const long long tiles_xy = (long long)((nx + BP_TX - 1) / BP_TX) * ((ny + BP_TY - 1) / BP_TY);
@@ -1052,6 +1067,7 @@ static tsp_projector *make_sub_projector(const tsp_projector *pr, int z0, int z1
     g.vectors = vec.data();
     tsp_projector *sub = nullptr;
     if (create_projector_internal(&g, pr->march_axis.data(), &sub) != TSP_OK) return nullptr;
+    sub->pool_owner = pr->pool_owner ? pr->pool_owner : const_cast<tsp_projector *>(pr);
     return sub;
 }
 
@@ -1074,6 +1090,8 @@ static tsp_projector *make_fine_projector(const tsp_projector *pr, int vox_d, in
     g.vectors = vec.data();
     tsp_projector *fine = nullptr;
     if (create_projector_internal(&g, pr->march_axis.data(), &fine) != TSP_OK) return nullptr;
+    // the slabs / row blocks cut from it belong to `pr` (the fine projector itself is only a template)
+    fine->pool_owner = pr->pool_owner ? pr->pool_owner : const_cast<tsp_projector *>(pr);
     return fine;
 }
 
