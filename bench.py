@@ -204,6 +204,31 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+def bind_host_to_gpu(torch, local):
+    """Restrict this process to the CPUs NVML lists as local to its GPU (same NUMA node / PCIe root) while the pinned
+    host buffers of the end-to-end leg are allocated and used: torchrun does not bind its workers, and pinned pages on
+    the far socket cost host<->device bandwidth.  Returns (affinity to restore | None, description)."""
+    if os.environ.get("TSP_BENCH_NO_BIND") or not hasattr(os, "sched_setaffinity"):
+        return None, "none"
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        uuid = str(torch.cuda.get_device_properties(local).uuid)
+        h = pynvml.nvmlDeviceGetHandleByUUID(uuid if uuid.startswith("GPU-") else "GPU-" + uuid)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        near = {i for i in range(ncpu) if (int(words[i // 64]) >> (i % 64)) & 1}
+        before = os.sched_getaffinity(0)
+        cpus = near & before
+        if not cpus or cpus == before:
+            return None, f"unchanged ({len(before)} CPUs allowed, {len(near)} local to the GPU)"
+        os.sched_setaffinity(0, cpus)
+        return before, f"{len(cpus)} of {len(before)} allowed CPUs (NVML affinity of the GPU)"
+    except Exception as exc:  # no NVML / no permission: run unbound
+        return None, f"none ({type(exc).__name__})"
+
+
 def sharded_parity_check(ts, ShardedOperator, dev, world):
     """The angle- / z-sharded operator (NCCL all_gather / reduce_scatter, chunked overlap) against the single-GPU
     operator on a 128^3 x 96-angle cone problem: relative L2 of this rank's FP angle block and BP z-slab, max over
@@ -228,7 +253,7 @@ def sharded_parity_check(ts, ShardedOperator, dev, world):
     e_bp = torch.linalg.vector_norm(xb_slab - xb_ref) / torch.linalg.vector_norm(xb_ref)
     t = torch.stack([e_fp, e_bp]).float()
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return {"fp": float(t[0]), "bp": float(t[1]), "problem": f"cone {n}^3 x {na} angles x {n}x{3 * n // 2}, {S.chunks} z-chunks",
+    return {"fp": float(t[0]), "bp": float(t[1]), "problem": f"cone {n}^3 x {na} angles x {n}x{3 * n // 2}, {S.chunks} z-chunks, bp_exchange={S.bp_exchange}",
             "ranks": world}
 
 
@@ -331,7 +356,7 @@ def run_ours(args):
         """Kernels launched by this rank's projectors: the local operator and, at N > 1, the z-chunk sub-operators."""
         ops = {id(S.local): S.local}
         if world > 1:
-            ops.update({id(op): op for _, _, _, op in S.chunk_operators() if op is not None})
+            ops.update({id(op): op for op in S.bp_operators()})
         return sum(op.astra_projector.info().kernel_launches for op in ops.values())
 
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
@@ -370,6 +395,7 @@ def run_ours(args):
     nvox, npix = int(np.prod(A.domain_shape)), int(np.prod(A.range_shape))
     e2e = None
     if not args.skip_e2e:
+        restore, binding = bind_host_to_gpu(torch, local)
         try:
             e2e_steps = max(10, min(args.steps, 20))
             if world == 1:
@@ -442,10 +468,14 @@ def run_ours(args):
                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                    "path": "A(x) / A.T(y) on pinned numpy arrays (library host pipeline)" if world == 1 else
                            "pinned host shards <-> ShardedOperator (slab up -> FP -> block down | block up -> BP -> slab down; "
-                           "copies on side streams, one synchronize per step)"}
+                           "copies on side streams, one synchronize per step)",
+                   "host_cpu_binding": binding}
         except Exception as exc:  # keep the device-resident line even if the host leg cannot run (e.g. no pinned memory)
             print(f"[bench] host-array leg failed on rank {rank}: {exc!r}", file=sys.stderr)
             e2e = None
+        finally:
+            if restore is not None:
+                os.sched_setaffinity(0, restore)
 
     # ---- SIRT iterations / s on the same problem (device-resident)
     sirt_iters = max(2, min(args.steps, 5))
@@ -487,10 +517,20 @@ def run_ours(args):
     # kernel names from the projectors that actually ran: FP on the rank-local operator, BP on it too at N = 1 but on the
     # z-chunk sub-operators at N > 1 (ShardedOperator._bp_chunks)
     info = P.info()
-    bp_infos = [info] if world == 1 else [op.astra_projector.info() for _, _, _, op in S.chunk_operators() if op is not None]
+    bp_infos = [info] if world == 1 else [op.astra_projector.info() for op in S.bp_operators()]
     bp_name = "bp_tma_kernel" if all(i.bp_uses_tma for i in bp_infos) else "bp_kernel"
     fp_name = "fp_tma_kernel" if info.fp_uses_tma else "fp_cols_kernel"
     n_chunks = S.chunks
+    if world > 1 and S.bp_exchange == "rows":
+        lo_, hi_ = S.row_bounds[rank]
+        bp_scheme = (f"NCCL all_to_all of detector row bands (rank 0: rows {lo_}:{hi_} of {S.proj_shape[0]}) -> BP of all angles "
+                     "into the rank's z-slab")
+        sirt_scheme = ("sharded: all_gather of the slabs -> fused residual FP -> all_to_all of row bands -> BP of all angles "
+                       "into the rank's slab -> local update")
+    else:
+        bp_scheme = f"BP in {n_chunks} z-chunks -> NCCL reduce_scatter per chunk (overlapped)"
+        sirt_scheme = (f"sharded: fused residual FP; BP in {n_chunks} z-chunks, each chunk's NCCL reduce_scatter + update + "
+                       "all_gather on a side stream behind the next chunk's kernel")
 
     # ---- N > 1: the sharded operator against the single-GPU operator on a small problem (every rank, max over ranks)
     sharded_parity = None
@@ -549,7 +589,7 @@ def run_ours(args):
                    "phantom": "hollow_box", "l2": ("inputs (4.3 GB + 9.1 GB) larger than L2" if big else
                                                    "inputs (537 MB + 1132 MB) larger than L2"),
                    "parallelism": "single GPU" if world == 1 else
-                   f"angle-sharded x{world}, z-sharded volume: NCCL all_gather -> FP; BP in {n_chunks} z-chunks -> NCCL reduce_scatter per chunk (overlapped)"},
+                   f"angle-sharded x{world}, z-sharded volume: NCCL all_gather -> FP; {bp_scheme}"},
         "fp_ms": fp_ms, "bp_ms": bp_ms,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / peaks["hbm_gbs"], "traffic": t_dom,
@@ -559,8 +599,7 @@ def run_ours(args):
         "e2e": e2e,
         "sirt": {"iters_per_s": 1e3 / sirt_ms, "ms_per_iter": sirt_ms, "iterations": sirt_iters,
                  "path": "tsp_sirt (fused epilogues)" if world == 1 else
-                 f"sharded: fused residual FP; BP in {n_chunks} z-chunks, each chunk's NCCL reduce_scatter + update + "
-                 "all_gather on a side stream behind the next chunk's kernel"},
+                 sirt_scheme},
         "cfg4_sirt": cfg4,
         "sharded_parity_rel_l2": sharded_parity,
         "gpu_launches": int(launches),

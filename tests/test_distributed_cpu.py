@@ -68,9 +68,12 @@ def _worker(rank, world, port, tmpdir):
         recs = []
         # chunks = 1: contiguous slabs, one collective per call; chunks = 2: interleaved pieces, the
         # overlapped exchange (9 slices over 2 x 2 pieces of 3: the last piece is all padding)
-        for chunks in (1, 2):
-            S = ShardedOperator(vg, pg, make_local=OracleOperator, chunks=chunks)
-            assert (S.angle_lo, S.angle_hi) == (lo, hi) and S.chunks == chunks
+        for chunks, mode in ((1, "volume"), (2, "volume"), (1, "rows")):
+            S = ShardedOperator(vg, pg, make_local=OracleOperator, chunks=chunks, bp_exchange=mode)
+            assert (S.angle_lo, S.angle_hi) == (lo, hi) and S.chunks == chunks and S.bp_exchange == mode
+            if mode == "rows":    # every rank back-projects all angles from a band of rows; the bands overlap
+                assert len(S.bp_operators()) == 1 and S.row_bounds[0][0] == 0 and S.row_bounds[1][1] == pg.det_shape[0]
+                assert S.row_bounds[0][1] > S.row_bounds[1][0] > 0
             if chunks == 1:
                 assert (S.z_lo, S.z_hi) == ((0, 5) if rank == 0 else (5, 9)) and S.slab_geometry().shape[0] == S.z_hi - S.z_lo
             else:
@@ -90,6 +93,9 @@ def _worker(rank, world, port, tmpdir):
             # SIRT: sharded == single-process (compared below), both layouts agree
             recs.append(S.gather_volume(sirt(S, y_full[:, lo:hi, :].contiguous(), 4)))
         torch.testing.assert_close(recs[0], recs[1], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(recs[0], recs[2], rtol=1e-4, atol=1e-5)
+        with pytest.raises(ValueError):
+            ShardedOperator(vg, pg, make_local=OracleOperator, chunks=2, bp_exchange="rows")
         rec = recs[1]
         torch.save(rec, os.path.join(tmpdir, f"rec{rank}.pt"))
         with pytest.raises(ValueError):
@@ -138,6 +144,41 @@ def test_single_process_sharded_operator_is_identity_wrapper():
     torch.testing.assert_close(S(x), OracleOperator(vg, pg)(x))
     with pytest.raises(TypeError):
         ShardedOperator(vg.to_vec(), pg)
+
+
+def test_slab_row_bounds_and_cropped_geometry(monkeypatch):
+    """The row band of a z-slab holds every bilinear tap of every voxel of the slab (brute force over the voxel
+    centres), is tight to a few rows, and the cropped geometry addresses the same pixels."""
+    from tomosipo_b200.distributed import crop_detector_rows, default_bp_exchange, slab_row_bounds
+
+    vg = ts.volume(shape=(24, 16, 20), size=(2.4, 1.6, 2.0))
+    for pg in (ts.cone(angles=11, shape=(40, 30), size=(6.0, 4.5), src_orig_dist=4, src_det_dist=7),
+               ts.parallel(angles=9, shape=(40, 30), size=(4.0, 3.0))):
+        V = pg.det_shape[0]
+        for z0, z1 in ((0, 6), (6, 12), (9, 15), (18, 24), (0, 24)):
+            sub = vg[z0:z1]
+            lo, hi = slab_row_bounds(sub, pg)
+            zz, yy, xx = np.meshgrid(*[np.arange(n) for n in sub.shape], indexing="ij")
+            centres = np.asarray(sub.lower_left_corner).reshape(1, 3) + (np.stack([zz, yy, xx], -1).reshape(-1, 3) + 0.5) * np.asarray(sub.voxel_size)[None]
+            v = np.concatenate([pg.to_vec().project_point(tuple(c))[:, 0] for c in centres]) + V / 2.0
+            t0, t1 = int(np.floor(v.min() - 0.5)), int(np.floor(v.max() - 0.5)) + 1      # first / last tap row
+            assert lo <= max(t0, 0) and min(t1, V - 1) < hi
+            assert max(t0, 0) - lo <= 4 and hi - 1 - min(t1, V - 1) <= 4
+            if hi - lo < V:
+                sub_pg = crop_detector_rows(pg, lo, hi)
+                assert tuple(sub_pg.det_shape) == (hi - lo, pg.det_shape[1]) and sub_pg.num_angles == pg.num_angles
+                p = centres[len(centres) // 3]
+                a, b = pg.to_vec().project_point(tuple(p)), sub_pg.project_point(tuple(p))
+                np.testing.assert_allclose(a[:, 0] + V / 2.0 - lo, b[:, 0] + (hi - lo) / 2.0, atol=1e-9)
+                np.testing.assert_allclose(a[:, 1], b[:, 1], atol=1e-9)
+    monkeypatch.delenv("TSP_SHARD_BP", raising=False)
+    big = ts.volume(shape=(64, 64, 64))
+    circ = ts.cone(angles=96, shape=(64, 96), size=(64 * 1.5, 96 * 1.5), src_orig_dist=256, src_det_dist=384)
+    assert default_bp_exchange(big, circ, 1) == "volume" and default_bp_exchange(big, circ, 8) == "rows"
+    tilted = ts.rotate(pos=0, axis=(0, 1, 0), angles=np.pi / 2) * circ.to_vec()     # scan around y: slabs see all rows
+    assert default_bp_exchange(big, tilted, 8) == "volume"
+    monkeypatch.setenv("TSP_SHARD_BP", "volume")
+    assert default_bp_exchange(big, circ, 8) == "volume"
 
 
 def test_default_chunks_and_piece_layout(monkeypatch):

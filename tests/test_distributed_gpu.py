@@ -30,9 +30,11 @@ def _worker(rank, world, port, tmpdir):
         y_full, bp_full = A(x), A.T(w)
         recs = []
         # chunks = 1: contiguous slabs, one collective per call; chunks = 3: interleaved pieces with the
-        # exchange overlapped chunk by chunk on a second stream (50 slices: padded pieces)
-        for chunks in (1, 3):
-            S = ShardedOperator(vg, pg, chunks=chunks)
+        # exchange overlapped chunk by chunk on a second stream (50 slices: padded pieces); "rows": every rank
+        # back-projects all angles into its own slab from an all_to_all of detector row bands
+        for chunks, mode in ((1, "volume"), (3, "volume"), (1, "rows")):
+            S = ShardedOperator(vg, pg, chunks=chunks, bp_exchange=mode)
+            assert S.bp_exchange == mode and len(S.bp_operators()) == (1 if mode == "rows" else chunks)
             blk = slice(S.angle_lo, S.angle_hi)
             y_blk = S(S.scatter_volume(x))
             assert torch.equal(y_blk, y_full[:, blk, :])                    # FP per angle is independent: bit-exact
@@ -46,6 +48,7 @@ def _worker(rank, world, port, tmpdir):
             torch.testing.assert_close(r_fused, Rb * (S.local(x) - yb), rtol=1e-5, atol=1e-6)
             recs.append(S.gather_volume(sirt(S, yb, 5)))
         assert float(torch.linalg.vector_norm(recs[0] - recs[1]) / torch.linalg.vector_norm(recs[0])) < 1e-5
+        assert float(torch.linalg.vector_norm(recs[0] - recs[2]) / torch.linalg.vector_norm(recs[0])) < 1e-5
         rec = recs[1]
         if rank == 0:
             torch.save(rec.cpu(), os.path.join(tmpdir, "rec.pt"))

@@ -35,6 +35,18 @@ all-gather.  The residual ``R * (A x - y)`` is formed in the forward
 projector's store (``tsp_project_fused``).  ``K = 1`` is the plain scheme of
 the table (contiguous slabs, one collective per call).
 
+Row exchange (``bp_exchange="rows"``).  The backprojection can also be sharded
+by *volume*: every rank back-projects ALL angles into its own (contiguous)
+z-slab and nothing has to be summed across ranks.  A z-slab only sees a band of
+detector rows (:func:`slab_row_bounds`), so what is exchanged is that band of
+every other rank's angle block - an ``all_to_all`` of contiguous row ranges
+(the projection layout is ``[V, angles, U]``) - instead of partial volumes.
+The kernel then runs one launch over all angles on the slab (the per-CTA set-up
+and the output store are paid once per voxel tile instead of once per rank and
+chunk), there is no partial-volume buffer, and no collective competes with the
+kernel for SMs; the exchange itself is exposed.  :func:`default_bp_exchange`
+picks the scheme; ``TSP_SHARD_BP=rows|volume`` overrides it.
+
 (Measured on 8 x B200, profiles/r01_bench_n8_*.json: reducing each slab to its
 owner and broadcasting it back -- the first pipelining scheme tried -- loses to
 the un-overlapped collectives, because a reduce / broadcast of one slab uses
@@ -67,16 +79,67 @@ def default_chunks(nz, world):
     return 1
 
 
+def slab_row_bounds(volume_geometry, projection_geometry, margin=2):
+    """Detector rows ``[lo, hi)`` that a backprojection into ``volume_geometry`` (any angle of
+    ``projection_geometry``) can read: the projections of the box's corners bound those of its voxels
+    (the detector coordinate is a projective function of the position, the box is convex and in front
+    of the source), plus the bilinear taps and ``margin`` rows of slack.  The whole detector when a
+    corner does not project (source inside the slab's plane range)."""
+    pg = projection_geometry.to_vec()
+    V = pg.det_shape[0]
+    with np.errstate(all="ignore"):
+        v = np.stack([pg.project_point(tuple(c))[:, 0] for c in np.asarray(volume_geometry.corners).reshape(-1, 3)])
+    if not np.all(np.isfinite(v)):
+        return 0, V
+    lo = int(np.floor(v.min() + V / 2.0 - 0.5)) - margin
+    hi = int(np.ceil(v.max() + V / 2.0 + 0.5)) + 1 + margin
+    lo, hi = max(lo, 0), min(hi, V)
+    return (lo, hi) if hi > lo else (0, 0)
+
+
+def crop_detector_rows(projection_geometry, lo, hi):
+    """The vector geometry restricted to detector rows ``[lo, hi)`` (same pixels, same positions)."""
+    pg = projection_geometry.to_vec()
+    V, U = pg.det_shape
+    det_pos = pg.det_pos + ((lo + hi) / 2.0 - V / 2.0) * pg.det_v
+    if pg.is_cone:
+        return ts.cone_vec(shape=(hi - lo, U), src_pos=pg.src_pos, det_pos=det_pos, det_v=pg.det_v, det_u=pg.det_u)
+    return ts.parallel_vec(shape=(hi - lo, U), ray_dir=pg.ray_dir, det_pos=det_pos, det_v=pg.det_v, det_u=pg.det_u)
+
+
+def default_bp_exchange(volume_geometry, projection_geometry, world):
+    """``"rows"`` when the row bands the ranks would have to receive are not much larger (<= 1.25 x) than the
+    partial volumes a reduce_scatter would move (circular scans around z; every slab of a scan around another
+    axis sees the whole detector), else ``"volume"``."""
+    env = os.environ.get("TSP_SHARD_BP")
+    if env in ("rows", "volume"):
+        return env
+    if world == 1:
+        return "volume"
+    nz, ny, nx = volume_geometry.shape
+    pg = projection_geometry.to_vec()
+    rows = 0
+    for r in range(world):
+        lo, hi = shard_bounds(nz, world, r)
+        if hi > lo:
+            b = slab_row_bounds(volume_geometry[lo:hi], pg)
+            rows = max(rows, b[1] - b[0])
+    return "rows" if rows * pg.num_angles * pg.det_shape[1] <= 1.25 * nz * ny * nx else "volume"
+
+
 class ShardedOperator:
     """Angle-/z-sharded view of ``ts.operator(vg, pg)`` over a process group.
 
     ``make_local(vg, pg_block)`` builds the rank-local operator (default:
     ``ts.operator``); it only has to be callable as ``op(x, out=...)`` /
     ``op.T(y, out=...)`` on the arrays it is given.  ``chunks``: see the module
-    docstring (default :func:`default_chunks`).
+    docstring (default :func:`default_chunks`).  ``bp_exchange``: ``"volume"`` (reduce_scatter of partial
+    volumes), ``"rows"`` (all_to_all of detector row bands, contiguous slabs, ``chunks = 1``) or None
+    (:func:`default_bp_exchange`; an explicit ``chunks > 1`` selects ``"volume"``).
     """
 
-    def __init__(self, volume_geometry, projection_geometry, group=None, make_local=None, device=None, chunks=None):
+    def __init__(self, volume_geometry, projection_geometry, group=None, make_local=None, device=None, chunks=None,
+                 bp_exchange=None):
         if not isinstance(volume_geometry, ts.geometry.VolumeGeometry):
             raise TypeError("ShardedOperator needs an axis-aligned VolumeGeometry (z-slab sharding).")
         self.group = group
@@ -92,6 +155,16 @@ class ShardedOperator:
         self._make_local = make_local or ts.operator
         self.local = self._make_local(volume_geometry, self.local_pg)
         nz, ny, nx = volume_geometry.shape
+        if bp_exchange is None:
+            bp_exchange = ("volume" if (chunks is not None and int(chunks) > 1)
+                           else default_bp_exchange(volume_geometry, pg, self.world))
+        if bp_exchange not in ("rows", "volume"):
+            raise ValueError(f"bp_exchange must be 'rows', 'volume' or None. Got {bp_exchange!r}")
+        self.bp_exchange = bp_exchange if self.world > 1 else "volume"
+        if self.bp_exchange == "rows":
+            if chunks is not None and int(chunks) > 1:
+                raise ValueError("bp_exchange='rows' shards the volume in contiguous slabs (chunks = 1)")
+            chunks = 1
         self.chunks = default_chunks(nz, self.world) if chunks is None else (max(1, int(chunks)) if self.world > 1 else 1)
         self.piece_nz = -(-nz // (self.chunks * self.world))  # pieces are padded to equal height for the collectives
         self.chunk_nz = self.piece_nz * self.world
@@ -109,6 +182,18 @@ class ShardedOperator:
         self._chunk_ops = None
         self._comm_stream = None
         self._transpose = _ShardedTranspose(self)
+        self.angle_bounds = [shard_bounds(pg.num_angles, self.world, r) for r in range(self.world)]
+        self.row_bounds = None    # rows mode: detector rows [lo, hi) every rank's slab reads
+        self._row_op = None
+        self._rows = self._row_staging = None
+        if self.bp_exchange == "rows":
+            self.row_bounds = []
+            for r in range(self.world):
+                lo, hi = self.piece_bounds(0, r)
+                self.row_bounds.append(slab_row_bounds(volume_geometry[lo:hi], pg) if hi > lo else (0, 0))
+            lo, hi = self.row_bounds[self.rank]
+            if hi > lo and self.z_hi > self.z_lo:
+                self._row_op = self._make_local(volume_geometry[self.z_lo:self.z_hi], crop_detector_rows(pg, lo, hi))
         # The exchange only overlaps the kernels if its CTAs are scheduled ahead of the backprojector's
         # queued ones: NCCL must run on high-priority streams.  With the default group that is a
         # construction-time option the caller may not have set, so the overlapped scheme talks over its
@@ -223,6 +308,12 @@ class ShardedOperator:
             self._chunk_ops = ops
         return self._chunk_ops
 
+    def bp_operators(self):
+        """The rank-local operators whose transposes run in ``A.T`` (for launch counts / kernel records)."""
+        if self.bp_exchange == "rows":
+            return [self._row_op] if self._row_op is not None else []
+        return [op for _, _, _, op in self.chunk_operators() if op is not None]
+
     def _streams(self, like):
         """(compute stream, communication stream) on CUDA, (None, None) on CPU."""
         if not like.is_cuda:
@@ -261,6 +352,49 @@ class ShardedOperator:
         else:  # gloo has no reduce_scatter: all_reduce, then keep the own piece
             dist.all_reduce(src, op=dist.ReduceOp.SUM, group=self.group)
             piece.copy_(src.view(self.world, self.piece_nz, *self.slab_shape[1:])[self.rank])
+
+    def _exchange_rows(self, y_block):
+        """``[rows of this rank's band, all angles, U]`` from every rank's angle block: rank ``q`` receives rows
+        ``row_bounds[q]`` of each block (contiguous: rows are the outermost axis) and interleaves the blocks by angle."""
+        lo, hi = self.row_bounds[self.rank]
+        U = self.proj_shape[2]
+        n_angles = self.angle_bounds[-1][1]
+        if self._rows is None or self._rows.device != y_block.device:
+            self._rows = torch.empty((hi - lo, n_angles, U), dtype=torch.float32, device=y_block.device)
+            self._row_staging = torch.empty((hi - lo) * n_angles * U, dtype=torch.float32, device=y_block.device)
+        y_block = y_block.contiguous()
+        # the own block goes straight into place; empty tensors stand in for it in the exchange
+        none = y_block[:0]
+        send = [none if q == self.rank else y_block[a:b] for q, (a, b) in enumerate(self.row_bounds)]
+        recv, off = [], 0
+        for q, (a, b) in enumerate(self.angle_bounds):
+            n = 0 if q == self.rank else (hi - lo) * (b - a) * U
+            recv.append(self._row_staging[off: off + n].view(hi - lo if n else 0, b - a, U))
+            off += n
+        if self._nccl():
+            dist.all_to_all(recv, send, group=self.group)
+        else:  # gloo has no all_to_all: pairwise, lower rank sends first
+            for q in range(self.world):
+                if q == self.rank:
+                    continue
+                ops = [lambda: dist.send(send[q].contiguous(), q, group=self.group) if send[q].numel() else None,
+                       lambda: dist.recv(recv[q], q, group=self.group) if recv[q].numel() else None]
+                for op in (ops if self.rank < q else ops[::-1]):
+                    op()
+        for q, ((a, b), part) in enumerate(zip(self.angle_bounds, recv)):
+            self._rows[:, a:b].copy_(y_block[lo:hi] if q == self.rank else part)
+        return self._rows
+
+    def _bp_rows(self, y_block, out):
+        rows = self._exchange_rows(y_block)
+        valid = self.z_hi - self.z_lo
+        if self._row_op is None:
+            out.zero_()
+            return out
+        self._row_op.T(rows, out=out[:valid])
+        if valid < out.shape[0]:
+            out[valid:].zero_()
+        return out
 
     def _bp_chunks(self, y_block, partial, after_chunk):
         """Back-project chunk by chunk into ``partial``; ``after_chunk(c)`` is issued on the communication
@@ -328,6 +462,8 @@ class ShardedOperator:
             out = torch.empty(self.slab_shape, dtype=torch.float32, device=y_block.device)
         elif not out.is_contiguous():
             raise ValueError("out must be contiguous")
+        if self.bp_exchange == "rows":
+            return self._bp_rows(y_block, out)
         partial = self._partial_volume(y_block)
         self._bp_chunks(y_block, partial, lambda c: self._reduce_scatter_chunk(self._piece_view(out, c), partial, c))
         return out
@@ -427,6 +563,19 @@ def _sirt_overlapped(A, y, R, C, x_cur, y_tmp, num_iterations):
         raise ValueError("x must be contiguous")
     x_full = A._full_volume(y)
     x_full_t = A._transposed_volume(y)                     # None unless this rank's angles march along x
+    if A.bp_exchange == "rows":
+        # volume-sharded backprojection: nothing to sum across ranks, the update is local and the new slabs are
+        # all-gathered (and transposed) in front of the next fused residual
+        x_tmp = torch.empty_like(x_cur)
+        y = y.contiguous()
+        for _ in range(num_iterations):
+            A._all_gather_chunk(x_full, x_cur, 0)
+            if x_full_t is not None:
+                A._transpose_chunk(x_full, x_full_t, 0)
+            A.residual(x_full[: A.vol_shape[0]], y, R, y_tmp, x_full_t)
+            A._bp_rows(y_tmp, x_tmp)
+            x_cur.addcmul_(C, x_tmp, value=-1.0)
+        return x_cur
     for c in range(A.chunks):
         A._all_gather_chunk(x_full, x_cur, c)
         if x_full_t is not None:
