@@ -41,10 +41,10 @@ z-slab and nothing has to be summed across ranks.  A z-slab only sees a band of
 detector rows (:func:`slab_row_bounds`), so what is exchanged is that band of
 every other rank's angle block - an ``all_to_all`` of contiguous row ranges
 (the projection layout is ``[V, angles, U]``) - instead of partial volumes.
-The kernel then runs one launch over all angles on the slab (the per-CTA set-up
-and the output store are paid once per voxel tile instead of once per rank and
-chunk), there is no partial-volume buffer, and no collective competes with the
-kernel for SMs; the exchange itself is exposed.  :func:`default_bp_exchange`
+The kernel then runs one launch over all angles on the slab, there is no
+partial-volume buffer, nothing to reduce and no collective competing with the
+kernel for SMs; the exchange itself is exposed, and so is the all-gather of the
+updated slabs in :func:`sirt` (the chunked ``"volume"`` scheme hides both).  :func:`default_bp_exchange`
 picks the scheme; ``TSP_SHARD_BP=rows|volume`` overrides it.
 
 (Measured on 8 x B200, profiles/r01_bench_n8_*.json: reducing each slab to its
@@ -97,20 +97,28 @@ def slab_row_bounds(volume_geometry, projection_geometry, margin=2):
     return (lo, hi) if hi > lo else (0, 0)
 
 
-def crop_detector_rows(projection_geometry, lo, hi):
-    """The vector geometry restricted to detector rows ``[lo, hi)`` (same pixels, same positions)."""
+def crop_detector_rows(projection_geometry, lo, hi, angles=None):
+    """The vector geometry restricted to detector rows ``[lo, hi)`` (same pixels, same positions) and, optionally,
+    to the angles of an index array."""
     pg = projection_geometry.to_vec()
     V, U = pg.det_shape
-    det_pos = pg.det_pos + ((lo + hi) / 2.0 - V / 2.0) * pg.det_v
+    sel = slice(None) if angles is None else np.asarray(angles, dtype=np.int64)
+    det_v, det_u = pg.det_v[sel], pg.det_u[sel]
+    det_pos = pg.det_pos[sel] + ((lo + hi) / 2.0 - V / 2.0) * det_v
     if pg.is_cone:
-        return ts.cone_vec(shape=(hi - lo, U), src_pos=pg.src_pos, det_pos=det_pos, det_v=pg.det_v, det_u=pg.det_u)
-    return ts.parallel_vec(shape=(hi - lo, U), ray_dir=pg.ray_dir, det_pos=det_pos, det_v=pg.det_v, det_u=pg.det_u)
+        return ts.cone_vec(shape=(hi - lo, U), src_pos=pg.src_pos[sel], det_pos=det_pos, det_v=det_v, det_u=det_u)
+    return ts.parallel_vec(shape=(hi - lo, U), ray_dir=pg.ray_dir[sel], det_pos=det_pos, det_v=det_v, det_u=det_u)
 
 
 def default_bp_exchange(volume_geometry, projection_geometry, world):
-    """``"rows"`` when the row bands the ranks would have to receive are not much larger (<= 1.25 x) than the
-    partial volumes a reduce_scatter would move (circular scans around z; every slab of a scan around another
-    axis sees the whole detector), else ``"volume"``."""
+    """``"rows"`` or ``"volume"`` (module docstring) from what was measured on B200s:
+
+    * rows need bands that are not much larger (<= 1.25 x) than the partial volumes a reduce_scatter would move -
+      circular scans around z; every slab of a scan around another axis sees the whole detector;
+    * the chunked volume scheme loses about a millisecond per call to its sub-launches and to NCCL sharing the SMs,
+      whatever the size, and hides its whole exchange in SIRT; the row scheme leaves SIRT's all-gather exposed, a
+      cost that grows with the volume.  Rows win while a chunk launch of the volume scheme would be shorter than
+      about 12 ms (2.5e10 voxel updates): cfg 3 at any N, not cfg 4 up to N = 8."""
     env = os.environ.get("TSP_SHARD_BP")
     if env in ("rows", "volume"):
         return env
@@ -118,6 +126,8 @@ def default_bp_exchange(volume_geometry, projection_geometry, world):
         return "volume"
     nz, ny, nx = volume_geometry.shape
     pg = projection_geometry.to_vec()
+    if float(nz) * ny * nx * pg.num_angles / (world * default_chunks(nz, world)) > 2.5e10:
+        return "volume"
     rows = 0
     for r in range(world):
         lo, hi = shard_bounds(nz, world, r)
@@ -184,8 +194,14 @@ class ShardedOperator:
         self._transpose = _ShardedTranspose(self)
         self.angle_bounds = [shard_bounds(pg.num_angles, self.world, r) for r in range(self.world)]
         self.row_bounds = None    # rows mode: detector rows [lo, hi) every rank's slab reads
-        self._row_op = None
+        self._row_op = self._row_own = self._row_rest = None
         self._rows = self._row_staging = None
+        # rows mode, opt-in variant (library operator): the rank's own angle block is back-projected first (it needs no
+        # exchange), the all_to_all runs behind that launch and a second, additive launch takes the other ranks'
+        # bands.  Measured at N = 2, cfg 3: 24.08 vs 23.97 ms - the second launch's wave tail costs what the hidden
+        # exchange saves - so one launch over all angles is the default.
+        self._row_split = (self.bp_exchange == "rows" and make_local is None and self._nccl()
+                           and bool(os.environ.get("TSP_SHARD_ROWS_SPLIT")))
         if self.bp_exchange == "rows":
             self.row_bounds = []
             for r in range(self.world):
@@ -193,12 +209,19 @@ class ShardedOperator:
                 self.row_bounds.append(slab_row_bounds(volume_geometry[lo:hi], pg) if hi > lo else (0, 0))
             lo, hi = self.row_bounds[self.rank]
             if hi > lo and self.z_hi > self.z_lo:
-                self._row_op = self._make_local(volume_geometry[self.z_lo:self.z_hi], crop_detector_rows(pg, lo, hi))
+                slab_vg = volume_geometry[self.z_lo:self.z_hi]
+                if self._row_split:
+                    own = np.arange(self.angle_lo, self.angle_hi)
+                    rest = np.concatenate([np.arange(0, self.angle_lo), np.arange(self.angle_hi, pg.num_angles)])
+                    self._row_own = ts.operator(slab_vg, crop_detector_rows(pg, lo, hi, own))
+                    self._row_rest = ts.operator(slab_vg, crop_detector_rows(pg, lo, hi, rest), additive=True)
+                else:
+                    self._row_op = self._make_local(slab_vg, crop_detector_rows(pg, lo, hi))
         # The exchange only overlaps the kernels if its CTAs are scheduled ahead of the backprojector's
         # queued ones: NCCL must run on high-priority streams.  With the default group that is a
         # construction-time option the caller may not have set, so the overlapped scheme talks over its
         # own communicator (measured at N = 8 without it: zero overlap, profiles/r01_sirt_breakdown_n8.txt).
-        if group is None and self.chunks > 1 and self._nccl():
+        if group is None and (self.chunks > 1 or self._row_split) and self._nccl():
             opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
             self.group = dist.new_group(backend="nccl", pg_options=opts)
 
@@ -311,7 +334,7 @@ class ShardedOperator:
     def bp_operators(self):
         """The rank-local operators whose transposes run in ``A.T`` (for launch counts / kernel records)."""
         if self.bp_exchange == "rows":
-            return [self._row_op] if self._row_op is not None else []
+            return [op for op in (self._row_op, self._row_own, self._row_rest) if op is not None]
         return [op for _, _, _, op in self.chunk_operators() if op is not None]
 
     def _streams(self, like):
@@ -353,17 +376,17 @@ class ShardedOperator:
             dist.all_reduce(src, op=dist.ReduceOp.SUM, group=self.group)
             piece.copy_(src.view(self.world, self.piece_nz, *self.slab_shape[1:])[self.rank])
 
-    def _exchange_rows(self, y_block):
-        """``[rows of this rank's band, all angles, U]`` from every rank's angle block: rank ``q`` receives rows
-        ``row_bounds[q]`` of each block (contiguous: rows are the outermost axis) and interleaves the blocks by angle."""
+    def _exchange_rows(self, y_block, with_own=True):
+        """``[rows of this rank's band, angles, U]`` from every rank's angle block: rank ``q`` receives rows
+        ``row_bounds[q]`` of each block (contiguous: rows are the outermost axis) and interleaves the blocks by angle
+        (all angles, or all but the rank's own block)."""
         lo, hi = self.row_bounds[self.rank]
         U = self.proj_shape[2]
-        n_angles = self.angle_bounds[-1][1]
+        n_angles = self.angle_bounds[-1][1] - (0 if with_own else self.angle_hi - self.angle_lo)
         if self._rows is None or self._rows.device != y_block.device:
             self._rows = torch.empty((hi - lo, n_angles, U), dtype=torch.float32, device=y_block.device)
             self._row_staging = torch.empty((hi - lo) * n_angles * U, dtype=torch.float32, device=y_block.device)
-        y_block = y_block.contiguous()
-        # the own block goes straight into place; empty tensors stand in for it in the exchange
+        # the own block never travels; empty tensors stand in for it in the exchange
         none = y_block[:0]
         send = [none if q == self.rank else y_block[a:b] for q, (a, b) in enumerate(self.row_bounds)]
         recv, off = [], 0
@@ -381,17 +404,40 @@ class ShardedOperator:
                        lambda: dist.recv(recv[q], q, group=self.group) if recv[q].numel() else None]
                 for op in (ops if self.rank < q else ops[::-1]):
                     op()
+        at = 0
         for q, ((a, b), part) in enumerate(zip(self.angle_bounds, recv)):
-            self._rows[:, a:b].copy_(y_block[lo:hi] if q == self.rank else part)
+            if q == self.rank and not with_own:
+                continue
+            self._rows[:, at: at + b - a].copy_(y_block[lo:hi] if q == self.rank else part)
+            at += b - a
         return self._rows
 
     def _bp_rows(self, y_block, out):
-        rows = self._exchange_rows(y_block)
+        """``out`` = the rank's z-slab of ``A^T y``: all angles, from the exchanged row band."""
         valid = self.z_hi - self.z_lo
-        if self._row_op is None:
-            out.zero_()
-            return out
-        self._row_op.T(rows, out=out[:valid])
+        y_block = y_block.contiguous()
+        compute, comm = self._streams(y_block)
+        if self._row_split and comm is not None:
+            lo, hi = self.row_bounds[self.rank]
+            comm.wait_stream(compute)                      # producer of y_block, last reader of the band buffer
+            with torch.cuda.stream(comm):
+                rest = self._exchange_rows(y_block, with_own=False)
+                ev = torch.cuda.Event()
+                ev.record(comm)
+            y_block.record_stream(comm)
+            if self._row_own is None:
+                compute.wait_event(ev)
+                out.zero_()
+                return out
+            self._row_own.T(y_block[lo:hi], out=out[:valid])      # own angles: no exchange needed
+            compute.wait_event(ev)
+            self._row_rest.T(rest, out=out[:valid])               # += the other ranks' angles
+        else:
+            rows = self._exchange_rows(y_block)
+            if self._row_op is None:
+                out.zero_()
+                return out
+            self._row_op.T(rows, out=out[:valid])
         if valid < out.shape[0]:
             out[valid:].zero_()
         return out
