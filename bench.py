@@ -523,9 +523,11 @@ def run_ours(args):
     n_chunks = S.chunks
     if world > 1 and S.bp_exchange == "rows":
         lo_, hi_ = S.row_bounds[rank]
-        bp_scheme = (f"NCCL all_to_all of detector row bands (rank 0: rows {lo_}:{hi_} of {S.proj_shape[0]}) -> BP of all angles "
+        how = ("stored by the ranks into each other's buffers over NVLink (tsp_push_rows, CUDA IPC)" if S._peer
+               else "exchanged by NCCL all_to_all")
+        bp_scheme = (f"detector row bands (rank 0: rows {lo_}:{hi_} of {S.proj_shape[0]}) {how} -> BP of all angles "
                      "into the rank's z-slab")
-        sirt_scheme = ("sharded: all_gather of the slabs -> fused residual FP -> all_to_all of row bands -> BP of all angles "
+        sirt_scheme = ("sharded: all_gather of the slabs -> fused residual FP -> row bands to the peers -> BP of all angles "
                        "into the rank's slab -> local update")
     else:
         bp_scheme = f"BP in {n_chunks} z-chunks -> NCCL reduce_scatter per chunk (overlapped)"

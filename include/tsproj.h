@@ -197,6 +197,27 @@ int tsp_fp_pre_transposed(tsp_projector *projector, const void *vol, const void 
                           const void *mul, int device, void *cuda_stream);
 
 /*
+ * Peer memory for the multi-GPU operator (one process per GPU; the reference has no multi-GPU path for device arrays:
+ * "you must distribute the data over multiple GPUs yourself", doc/topics/operator.rst:246-249).  Its backprojection
+ * by row exchange (tomosipo_b200/distributed.py) needs, on every rank, a band of detector rows of every other rank's
+ * angle block; the ranks store those rows straight into each other's band buffers over NVLink:
+ *   tsp_peer_alloc   cudaMalloc a buffer on `device` and export its 64-byte CUDA IPC handle
+ *   tsp_peer_open    map another process's buffer (its handle) into this process, peer access enabled lazily
+ *   tsp_peer_close   unmap it;  tsp_peer_free: release an own buffer (after the peers have closed it)
+ *   tsp_push_rows    n_jobs strided copies in one kernel, asynchronous on the stream: job k copies rows[k] rows of
+ *                    width[k] floats from src[k] (row pitch src_pitch[k] floats) to dst[k] (row pitch dst_pitch[k]);
+ *                    dst may be peer memory.  `projector` (may be NULL) only counts the launch.
+ * Completion across ranks is the caller's business (a collective on the same stream).
+ */
+int tsp_peer_alloc(size_t bytes, int device, void **ptr, void *handle64);
+int tsp_peer_open(const void *handle64, int device, void **ptr);
+int tsp_peer_close(void *ptr, int device);
+int tsp_peer_free(void *ptr, int device);
+int tsp_push_rows(tsp_projector *projector, int n_jobs, const void *const *src, void *const *dst, const int64_t *rows,
+                  const int64_t *width, const int64_t *src_pitch, const int64_t *dst_pitch, int device,
+                  void *cuda_stream);
+
+/*
  * Page-locked host buffers for arrays the host-array path creates itself (the operator's outputs and the float32
  * copies of float64 inputs; reference tomosipo/links/numpy.py:26-32,121-144 allocates them with numpy): transfers
  * from / to pageable memory do not overlap the kernels.  Freed buffers are cached by size (TSP_PINNED_CACHE_MB,

@@ -32,13 +32,17 @@ def _worker(rank, world, port, tmpdir):
         # chunks = 1: contiguous slabs, one collective per call; chunks = 3: interleaved pieces with the
         # exchange overlapped chunk by chunk on a second stream (50 slices: padded pieces); "rows": every rank
         # back-projects all angles into its own slab from an all_to_all of detector row bands
-        # (one launch over all angles; or, opt-in, the own angle block first with the exchange behind it and the
-        # other blocks added by a second launch)
-        for chunks, mode, split in ((1, "volume", ""), (3, "volume", ""), (1, "rows", ""), (1, "rows", "1")):
-            os.environ["TSP_SHARD_ROWS_SPLIT"] = split
+        # (row bands stored into the peers' buffers over NVLink by tsp_push_rows; or exchanged by NCCL all_to_all;
+        # or, opt-in, the own angle block first with the all_to_all behind it and the other blocks added by a second launch)
+        variants = ((1, "volume", {}), (3, "volume", {}), (1, "rows", {}), (1, "rows", {"TSP_SHARD_NO_P2P": "1"}),
+                    (1, "rows", {"TSP_SHARD_ROWS_SPLIT": "1"}))
+        for chunks, mode, env in variants:
+            for key in ("TSP_SHARD_NO_P2P", "TSP_SHARD_ROWS_SPLIT"):
+                os.environ.pop(key, None)
+            os.environ.update(env)
             S = ShardedOperator(vg, pg, chunks=chunks, bp_exchange=mode)
             assert S.bp_exchange == mode
-            assert len(S.bp_operators()) == (chunks if mode == "volume" else 2 if split else 1)
+            assert len(S.bp_operators()) == (chunks if mode == "volume" else 2 if "TSP_SHARD_ROWS_SPLIT" in env else 1)
             blk = slice(S.angle_lo, S.angle_hi)
             y_blk = S(S.scatter_volume(x))
             assert torch.equal(y_blk, y_full[:, blk, :])                    # FP per angle is independent: bit-exact
@@ -51,8 +55,18 @@ def _worker(rank, world, port, tmpdir):
             r_fused = S.residual(x.contiguous(), yb, Rb, torch.empty_like(yb))
             torch.testing.assert_close(r_fused, Rb * (S.local(x) - yb), rtol=1e-5, atol=1e-6)
             recs.append(S.gather_volume(sirt(S, yb, 5)))
+            if mode == "rows" and not env:
+                assert S._peer, "the peer-memory exchange was not used"
+                launches = S.local.astra_projector.info().kernel_launches
+                S.T(w[:, blk, :].contiguous())
+                assert S.local.astra_projector.info().kernel_launches == launches + 1       # tsp_push_rows
+                S.close()
+                assert S._peer is None
+            elif mode == "rows":
+                assert not S._peer
         assert float(torch.linalg.vector_norm(recs[0] - recs[1]) / torch.linalg.vector_norm(recs[0])) < 1e-5
-        os.environ.pop("TSP_SHARD_ROWS_SPLIT", None)
+        for key in ("TSP_SHARD_NO_P2P", "TSP_SHARD_ROWS_SPLIT"):
+            os.environ.pop(key, None)
         for other in recs[2:]:
             assert float(torch.linalg.vector_norm(recs[0] - other) / torch.linalg.vector_norm(recs[0])) < 1e-5
         rec = recs[1]

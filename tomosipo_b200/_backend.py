@@ -83,6 +83,11 @@ EXPORTED_SYMBOLS = (
     "tsp_fp_transposed_elems",
     "tsp_transpose_slices",
     "tsp_fp_pre_transposed",
+    "tsp_peer_alloc",
+    "tsp_peer_open",
+    "tsp_peer_close",
+    "tsp_peer_free",
+    "tsp_push_rows",
 )
 
 
@@ -149,6 +154,18 @@ def lib():
         L.tsp_fp_pre_transposed.restype = ctypes.c_int
         L.tsp_host_alloc.argtypes = [ctypes.c_size_t]
         L.tsp_host_alloc.restype = vp
+        L.tsp_peer_alloc.argtypes = [ctypes.c_size_t, ctypes.c_int, ctypes.POINTER(vp), ctypes.c_char_p]
+        L.tsp_peer_alloc.restype = ctypes.c_int
+        L.tsp_peer_open.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(vp)]
+        L.tsp_peer_open.restype = ctypes.c_int
+        L.tsp_peer_close.argtypes = [vp, ctypes.c_int]
+        L.tsp_peer_close.restype = ctypes.c_int
+        L.tsp_peer_free.argtypes = [vp, ctypes.c_int]
+        L.tsp_peer_free.restype = ctypes.c_int
+        i64p = ctypes.POINTER(ctypes.c_int64)
+        L.tsp_push_rows.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(vp), i64p, i64p, i64p, i64p,
+                                    ctypes.c_int, vp]
+        L.tsp_push_rows.restype = ctypes.c_int
         L.tsp_host_free.argtypes = [vp]
         L.tsp_host_free.restype = None
         f64p = ctypes.POINTER(ctypes.c_double)
@@ -272,6 +289,10 @@ class Projector:
         _check(lib().tsp_fp_transposed_elems(self._handle, ctypes.byref(n)))
         return int(n.value)
 
+    def push_rows(self, jobs, device=0, stream=0):
+        """One kernel of strided row copies (``tsp_push_rows``); destinations may be peer memory."""
+        push_rows(jobs, device=device, stream=stream, projector=self)
+
     def transpose_slices(self, vol_ptr, vol_t_ptr, z0, z1, device=0, stream=0):
         vp = ctypes.c_void_p
         _check(lib().tsp_transpose_slices(self._handle, vp(vol_ptr), vp(vol_t_ptr), int(z0), int(z1), int(device), vp(stream)))
@@ -328,3 +349,46 @@ class Projector:
         axes = np.zeros(self.n_angles, dtype=np.int32)
         _check(lib().tsp_projector_marching_axes(self._handle, axes.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))))
         return axes
+
+
+# ------------------------------------------------------------ peer memory --
+def peer_alloc(nbytes, device):
+    """``(device pointer, 64-byte CUDA IPC handle)`` of a new cudaMalloc'ed buffer (``tsp_peer_alloc``)."""
+    ptr = ctypes.c_void_p()
+    handle = ctypes.create_string_buffer(64)
+    _check(lib().tsp_peer_alloc(int(nbytes), int(device), ctypes.byref(ptr), handle))
+    return int(ptr.value), handle.raw
+
+
+def peer_open(handle, device):
+    """Device pointer of another process's buffer mapped into this one (``tsp_peer_open``)."""
+    ptr = ctypes.c_void_p()
+    _check(lib().tsp_peer_open(bytes(handle), int(device), ctypes.byref(ptr)))
+    return int(ptr.value)
+
+
+def peer_close(ptr, device):
+    _check(lib().tsp_peer_close(ctypes.c_void_p(ptr), int(device)))
+
+
+def peer_free(ptr, device):
+    _check(lib().tsp_peer_free(ctypes.c_void_p(ptr), int(device)))
+
+
+def push_rows(jobs, device=0, stream=0, projector=None):
+    """``jobs``: ``[(src_ptr, dst_ptr, rows, width, src_pitch, dst_pitch)]`` in floats; one launch, asynchronous."""
+    n = len(jobs)
+    vp = ctypes.c_void_p
+    src = (vp * n)(*[vp(j[0]) for j in jobs])
+    dst = (vp * n)(*[vp(j[1]) for j in jobs])
+    cols = [(ctypes.c_int64 * n)(*[int(j[k]) for j in jobs]) for k in (2, 3, 4, 5)]
+    _check(lib().tsp_push_rows(projector._handle if projector is not None else None, n, src, dst, *cols, int(device), vp(stream)))
+
+
+class DeviceBuffer:
+    """A float32 device buffer owned by the library, visible to torch through ``__cuda_array_interface__``."""
+
+    def __init__(self, ptr, shape):
+        self.ptr, self.shape = int(ptr), tuple(int(v) for v in shape)
+        self.__cuda_array_interface__ = {"shape": self.shape, "typestr": "<f4", "data": (self.ptr, False), "version": 2,
+                                         "strides": None}

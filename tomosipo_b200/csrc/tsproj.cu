@@ -19,6 +19,7 @@
 #include "bp_kernels.cuh"
 #include "fp_kernels.cuh"
 #include "fdk_kernels.cuh"
+#include "peer_kernels.cuh"
 #include "fp_tma_kernels.cuh"
 #include "thin_kernels.cuh"
 #include "tsp_internal.h"
@@ -1781,6 +1782,104 @@ extern "C" int tsp_transpose_slices(tsp_projector *pr, const void *vol, void *vo
                                                                        (float *)vol_t + (size_t)z0 * g.nx * ny_pad, g.nx, g.ny, ny_pad);
     ++pr->launches;
     CUDA_TRY(cudaGetLastError());
+    return TSP_OK;
+}
+
+// ------------------------------------------------------------ peer memory --
+static int enter_device(DeviceGuard &guard, int device)
+{
+    const int ndev = tsp_device_count();
+    if (ndev == 0) return fail(TSP_ERR_CUDA, "no CUDA device available (libtsproj has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(TSP_ERR_INVALID, "device %d out of range [0, %d)", device, ndev);
+    if (guard.enter(device) != 0) return fail(TSP_ERR_CUDA, "cannot switch to device %d", device);
+    return TSP_OK;
+}
+
+extern "C" int tsp_peer_alloc(size_t bytes, int device, void **ptr, void *handle64)
+{
+    if (!ptr || !handle64 || bytes == 0) return fail(TSP_ERR_INVALID, "NULL argument / empty buffer");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    DeviceGuard guard;
+    if (int rc = enter_device(guard, device)) return rc;
+    void *p = nullptr;
+    CUDA_TRY(cudaMalloc(&p, bytes));
+    cudaIpcMemHandle_t h;
+    const cudaError_t e = cudaIpcGetMemHandle(&h, p);
+    if (e != cudaSuccess) {
+        cudaFree(p);
+        return fail(TSP_ERR_CUDA, "cudaIpcGetMemHandle failed: %s", cudaGetErrorString(e));
+    }
+    memcpy(handle64, &h, sizeof h);
+    *ptr = p;
+    return TSP_OK;
+}
+
+extern "C" int tsp_peer_open(const void *handle64, int device, void **ptr)
+{
+    if (!ptr || !handle64) return fail(TSP_ERR_INVALID, "NULL argument");
+    DeviceGuard guard;
+    if (int rc = enter_device(guard, device)) return rc;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof h);
+    CUDA_TRY(cudaIpcOpenMemHandle(ptr, h, cudaIpcMemLazyEnablePeerAccess));
+    return TSP_OK;
+}
+
+extern "C" int tsp_peer_close(void *ptr, int device)
+{
+    if (!ptr) return TSP_OK;
+    DeviceGuard guard;
+    if (int rc = enter_device(guard, device)) return rc;
+    CUDA_TRY(cudaIpcCloseMemHandle(ptr));
+    return TSP_OK;
+}
+
+extern "C" int tsp_peer_free(void *ptr, int device)
+{
+    if (!ptr) return TSP_OK;
+    DeviceGuard guard;
+    if (int rc = enter_device(guard, device)) return rc;
+    CUDA_TRY(cudaFree(ptr));
+    return TSP_OK;
+}
+
+extern "C" int tsp_push_rows(tsp_projector *pr, int n_jobs, const void *const *src, void *const *dst, const int64_t *rows,
+                             const int64_t *width, const int64_t *src_pitch, const int64_t *dst_pitch, int device,
+                             void *cuda_stream)
+{
+    if (n_jobs < 0 || (n_jobs > 0 && (!src || !dst || !rows || !width || !src_pitch || !dst_pitch)))
+        return fail(TSP_ERR_INVALID, "NULL argument");
+    DeviceGuard guard;
+    if (int rc = enter_device(guard, device)) return rc;
+    for (int first = 0; first < n_jobs; first += PUSH_MAX_JOBS) {
+        PushArgs args;
+        int n = 0;
+        bool vec4 = true;
+        long long most = 0;
+        for (int k = first; k < n_jobs && n < PUSH_MAX_JOBS; ++k) {
+            if (rows[k] < 0 || width[k] < 0 || src_pitch[k] < width[k] || dst_pitch[k] < width[k])
+                return fail(TSP_ERR_INVALID, "job %d: rows %lld, width %lld, pitches %lld / %lld", k, (long long)rows[k],
+                            (long long)width[k], (long long)src_pitch[k], (long long)dst_pitch[k]);
+            if (rows[k] == 0 || width[k] == 0) continue;
+            if (!src[k] || !dst[k]) return fail(TSP_ERR_INVALID, "job %d: NULL buffer", k);
+            PushJob &j = args.job[n++];
+            j = {(const float *)src[k], (float *)dst[k], rows[k], width[k], src_pitch[k], dst_pitch[k]};
+            vec4 = vec4 && width[k] % 4 == 0 && src_pitch[k] % 4 == 0 && dst_pitch[k] % 4 == 0 &&
+                   (uintptr_t)src[k] % 16 == 0 && (uintptr_t)dst[k] % 16 == 0;
+            most = std::max<long long>(most, rows[k] * width[k]);
+        }
+        if (n == 0) continue;
+        // enough CTAs to fill the SMs across all jobs, no more than one pass of the largest job needs
+        const long long per_cta = 512LL * (vec4 ? 16 : 4);
+        const int bx = (int)std::max<long long>(1, std::min<long long>((most + per_cta - 1) / per_cta, (4 * 148 + n - 1) / n));
+        dim3 grid(bx, n);
+        if (vec4)
+            push_rows_kernel<4><<<grid, 512, 0, (cudaStream_t)cuda_stream>>>(args);
+        else
+            push_rows_kernel<1><<<grid, 512, 0, (cudaStream_t)cuda_stream>>>(args);
+        if (pr) ++pr->launches;
+        CUDA_TRY(cudaGetLastError());
+    }
     return TSP_OK;
 }
 

@@ -196,6 +196,7 @@ class ShardedOperator:
         self.row_bounds = None    # rows mode: detector rows [lo, hi) every rank's slab reads
         self._row_op = self._row_own = self._row_rest = None
         self._rows = self._row_staging = None
+        self._peer = False        # not tried yet (None: unavailable, the NCCL all_to_all is used)
         # rows mode, opt-in variant (library operator): the rank's own angle block is back-projected first (it needs no
         # exchange), the all_to_all runs behind that launch and a second, additive launch takes the other ranks'
         # bands.  Measured at N = 2, cfg 3: 24.08 vs 23.97 ms - the second launch's wave tail costs what the hidden
@@ -376,10 +377,95 @@ class ShardedOperator:
             dist.all_reduce(src, op=dist.ReduceOp.SUM, group=self.group)
             piece.copy_(src.view(self.world, self.piece_nz, *self.slab_shape[1:])[self.rank])
 
+    # ------------------------------------------------- peer-memory exchange --
+    def _peer_setup(self, y_block):
+        """Two band buffers per rank (alternating calls), allocated by the library and mapped by every peer through
+        CUDA IPC; None when any rank cannot (then every rank uses the NCCL all_to_all)."""
+        from . import _backend as B
+
+        dev = y_block.device
+        lo, hi = self.row_bounds[self.rank]
+        shape = (hi - lo, self.angle_bounds[-1][1], self.proj_shape[2])
+        own, mapped, ok = [], [], 1.0
+        try:
+            own = [B.peer_alloc(max(1, int(np.prod(shape))) * 4, dev.index) for _ in range(2)]
+        except Exception:
+            ok = 0.0
+        handles = [None] * self.world
+        dist.all_gather_object(handles, [h for _, h in own] if ok else None, group=self.group)
+        ptrs = [[None] * self.world for _ in range(2)]
+        if ok and all(h is not None for h in handles):
+            try:
+                for q in range(self.world):
+                    for k in range(2):
+                        if q == self.rank:
+                            ptrs[k][q] = own[k][0]
+                        else:
+                            ptrs[k][q] = B.peer_open(handles[q][k], dev.index)
+                            mapped.append(ptrs[k][q])
+            except Exception:
+                ok = 0.0
+        else:
+            ok = 0.0
+        views = []
+        if ok:
+            views = [torch.as_tensor(B.DeviceBuffer(ptr, shape), device=dev) for ptr, _ in own]
+            if any(v.data_ptr() != ptr or v.device != dev for v, (ptr, _) in zip(views, own)):
+                ok = 0.0                                   # torch copied instead of wrapping the buffer
+        flag = torch.tensor([ok], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if float(flag.item()) < 1.0:                       # some rank failed: nobody uses peer memory
+            for ptr in mapped:
+                B.peer_close(ptr, dev.index)
+            dist.barrier(group=self.group)
+            for ptr, _ in own:
+                B.peer_free(ptr, dev.index)
+            return None
+        return {"ptrs": ptrs, "views": views, "turn": 0, "flag": torch.zeros(1, device=dev), "mapped": mapped,
+                "own": [ptr for ptr, _ in own], "device": dev.index}
+
+    def _exchange_rows_peer(self, y_block):
+        """The band of every rank's angle block, stored by the ranks themselves: one kernel of NVLink stores per rank
+        (``tsp_push_rows``) puts the rows each peer's slab reads into that peer's buffer at this rank's angle offset;
+        a one-element all_reduce on the same stream tells every rank that all stores have landed.  The buffers
+        alternate between calls: a rank may start storing for call k + 1 while a peer still back-projects call k."""
+        from . import _backend as B
+
+        P = self._peer
+        k = P["turn"]
+        P["turn"] = k ^ 1
+        U = self.proj_shape[2]
+        a_me, a_all = self.angle_hi - self.angle_lo, self.angle_bounds[-1][1]
+        base = y_block.data_ptr()
+        jobs = [(base + a * a_me * U * 4, P["ptrs"][k][q] + self.angle_lo * U * 4, b - a, a_me * U, a_me * U, a_all * U)
+                for q, (a, b) in enumerate(self.row_bounds) if b > a]
+        stream = torch.cuda.current_stream(y_block.device).cuda_stream
+        B.push_rows(jobs, device=P["device"], stream=stream, projector=getattr(self.local, "astra_projector", None))
+        dist.all_reduce(P["flag"], group=self.group)
+        return P["views"][k]
+
+    def close(self):
+        """Unmap the peers' band buffers and release the own ones (collective; optional - process exit does the same)."""
+        P, self._peer = self._peer, None
+        if P:
+            from . import _backend as B
+
+            torch.cuda.synchronize(P["device"])
+            for ptr in P["mapped"]:
+                B.peer_close(ptr, P["device"])
+            dist.barrier(group=self.group)
+            for ptr in P["own"]:
+                B.peer_free(ptr, P["device"])
+
     def _exchange_rows(self, y_block, with_own=True):
         """``[rows of this rank's band, angles, U]`` from every rank's angle block: rank ``q`` receives rows
         ``row_bounds[q]`` of each block (contiguous: rows are the outermost axis) and interleaves the blocks by angle
         (all angles, or all but the rank's own block)."""
+        if (with_own and self._peer is False and y_block.is_cuda and self._nccl() and y_block.dtype == torch.float32
+                and not os.environ.get("TSP_SHARD_NO_P2P")):
+            self._peer = self._peer_setup(y_block)
+        if with_own and self._peer and y_block.is_cuda and y_block.dtype == torch.float32 and y_block.is_contiguous():
+            return self._exchange_rows_peer(y_block)
         lo, hi = self.row_bounds[self.rank]
         U = self.proj_shape[2]
         n_angles = self.angle_bounds[-1][1] - (0 if with_own else self.angle_hi - self.angle_lo)
