@@ -523,8 +523,10 @@ def run_ours(args):
     n_chunks = S.chunks
     if world > 1 and S.bp_exchange == "rows":
         lo_, hi_ = S.row_bounds[rank]
-        how = ("stored by the ranks into each other's buffers over NVLink (tsp_push_rows, CUDA IPC)" if S._peer
-               else "exchanged by NCCL all_to_all")
+        how = ("exchanged by NCCL all_to_all" if not S._peer else
+               "stored into the peers' buffers over NVLink by the forward projector's own stores (tsp_fp_push, CUDA IPC buffers; "
+               "tsp_push_rows for arrays that did not come out of A(x))" if S._peer["fp_push"] else
+               "stored by the ranks into each other's buffers over NVLink (tsp_push_rows, CUDA IPC buffers)")
         bp_scheme = (f"detector row bands (rank 0: rows {lo_}:{hi_} of {S.proj_shape[0]}) {how} -> BP of all angles "
                      "into the rank's z-slab")
         sirt_scheme = ("sharded: all_gather of the slabs -> fused residual FP -> row bands to the peers -> BP of all angles "

@@ -207,12 +207,20 @@ int tsp_fp_pre_transposed(tsp_projector *projector, const void *vol, const void 
  *   tsp_push_rows    n_jobs strided copies in one kernel, asynchronous on the stream: job k copies rows[k] rows of
  *                    width[k] floats from src[k] (row pitch src_pitch[k] floats) to dst[k] (row pitch dst_pitch[k]);
  *                    dst may be peer memory.  `projector` (may be NULL) only counts the launch.
+ *   tsp_fp_push      tsp_fp_pre_transposed whose store also writes every value of detector row v in
+ *                    [row_lo[q], row_hi[q]) to peer_base[q][(v - row_lo[q]) * peer_pitch + angle * det_cols + u]
+ *                    (q < n_peers <= 16; peer_base[q] already points at this rank's first angle in rank q's band
+ *                    buffer): the exchange rides on the projector's own stores, tile by tile, and needs no pass of its
+ *                    own.  SET mode, no detector supersampling.
  * Completion across ranks is the caller's business (a collective on the same stream).
  */
 int tsp_peer_alloc(size_t bytes, int device, void **ptr, void *handle64);
 int tsp_peer_open(const void *handle64, int device, void **ptr);
 int tsp_peer_close(void *ptr, int device);
 int tsp_peer_free(void *ptr, int device);
+int tsp_fp_push(tsp_projector *projector, const void *vol, const void *vol_t, void *proj, const void *sub, const void *mul,
+                int n_peers, void *const *peer_base, const int32_t *row_lo, const int32_t *row_hi, int64_t peer_pitch,
+                int device, void *cuda_stream);
 int tsp_push_rows(tsp_projector *projector, int n_jobs, const void *const *src, void *const *dst, const int64_t *rows,
                   const int64_t *width, const int64_t *src_pitch, const int64_t *dst_pitch, int device,
                   void *cuda_stream);

@@ -34,10 +34,14 @@ def _worker(rank, world, port, tmpdir):
         # back-projects all angles into its own slab from an all_to_all of detector row bands
         # (row bands stored into the peers' buffers over NVLink by tsp_push_rows; or exchanged by NCCL all_to_all;
         # or, opt-in, the own angle block first with the all_to_all behind it and the other blocks added by a second launch)
-        variants = ((1, "volume", {}), (3, "volume", {}), (1, "rows", {}), (1, "rows", {"TSP_SHARD_NO_P2P": "1"}),
-                    (1, "rows", {"TSP_SHARD_ROWS_SPLIT": "1"}))
+        # default: the forward projector's own store fills the peers' buffers (tsp_fp_push), tsp_push_rows only for
+        # arrays that did not come out of the forward projection
+        env_keys = ("TSP_SHARD_NO_P2P", "TSP_SHARD_ROWS_SPLIT", "TSP_SHARD_NO_FP_PUSH")
+        variants = ((1, "volume", {}), (3, "volume", {}), (1, "rows", {}), (1, "rows", {"TSP_SHARD_NO_FP_PUSH": "1"}),
+                    (1, "rows", {"TSP_SHARD_NO_P2P": "1"}), (1, "rows", {"TSP_SHARD_ROWS_SPLIT": "1"}))
+        bp_of_fp = A.T(y_full)
         for chunks, mode, env in variants:
-            for key in ("TSP_SHARD_NO_P2P", "TSP_SHARD_ROWS_SPLIT"):
+            for key in env_keys:
                 os.environ.pop(key, None)
             os.environ.update(env)
             S = ShardedOperator(vg, pg, chunks=chunks, bp_exchange=mode)
@@ -55,17 +59,28 @@ def _worker(rank, world, port, tmpdir):
             r_fused = S.residual(x.contiguous(), yb, Rb, torch.empty_like(yb))
             torch.testing.assert_close(r_fused, Rb * (S.local(x) - yb), rtol=1e-5, atol=1e-6)
             recs.append(S.gather_volume(sirt(S, yb, 5)))
-            if mode == "rows" and not env:
+            # A.T(A(x)): with the fused exchange the backprojection finds its rows already in place
+            count = lambda: S.local.astra_projector.info().kernel_launches
+            y_blk = S(S.scatter_volume(x))
+            n0 = count()
+            slab = S.T(y_blk)
+            n1 = count()
+            torch.testing.assert_close(S.gather_volume(slab), bp_of_fp, rtol=1e-5, atol=1e-5 * float(bp_of_fp.max()))
+            y_blk = S(S.scatter_volume(x))
+            y_blk *= 2.0                                                    # modified since: must be exchanged again
+            torch.testing.assert_close(S.gather_volume(S.T(y_blk)), 2.0 * bp_of_fp, rtol=1e-5, atol=2e-5 * float(bp_of_fp.max()))
+            if mode == "rows" and (not env or "TSP_SHARD_NO_FP_PUSH" in env):
                 assert S._peer, "the peer-memory exchange was not used"
-                launches = S.local.astra_projector.info().kernel_launches
+                assert n1 - n0 == (0 if not env else 1)                     # tsp_push_rows only without the fused store
+                n0 = count()
                 S.T(w[:, blk, :].contiguous())
-                assert S.local.astra_projector.info().kernel_launches == launches + 1       # tsp_push_rows
+                assert count() == n0 + 1                                    # a foreign array: tsp_push_rows
                 S.close()
                 assert S._peer is None
             elif mode == "rows":
                 assert not S._peer
         assert float(torch.linalg.vector_norm(recs[0] - recs[1]) / torch.linalg.vector_norm(recs[0])) < 1e-5
-        for key in ("TSP_SHARD_NO_P2P", "TSP_SHARD_ROWS_SPLIT"):
+        for key in env_keys:
             os.environ.pop(key, None)
         for other in recs[2:]:
             assert float(torch.linalg.vector_norm(recs[0] - other) / torch.linalg.vector_norm(recs[0])) < 1e-5

@@ -88,6 +88,7 @@ EXPORTED_SYMBOLS = (
     "tsp_peer_close",
     "tsp_peer_free",
     "tsp_push_rows",
+    "tsp_fp_push",
 )
 
 
@@ -166,6 +167,10 @@ def lib():
         L.tsp_push_rows.argtypes = [vp, ctypes.c_int, ctypes.POINTER(vp), ctypes.POINTER(vp), i64p, i64p, i64p, i64p,
                                     ctypes.c_int, vp]
         L.tsp_push_rows.restype = ctypes.c_int
+        i32p = ctypes.POINTER(ctypes.c_int32)
+        L.tsp_fp_push.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_int, ctypes.POINTER(vp), i32p, i32p, ctypes.c_int64,
+                                  ctypes.c_int, vp]
+        L.tsp_fp_push.restype = ctypes.c_int
         L.tsp_host_free.argtypes = [vp]
         L.tsp_host_free.restype = None
         f64p = ctypes.POINTER(ctypes.c_double)
@@ -288,6 +293,17 @@ class Projector:
         n = ctypes.c_int64(0)
         _check(lib().tsp_fp_transposed_elems(self._handle, ctypes.byref(n)))
         return int(n.value)
+
+    def fp_push(self, vol_ptr, vol_t_ptr, proj_ptr, sub_ptr, mul_ptr, peers, pitch, device=0, stream=0):
+        """``fp_pre_transposed`` whose store also writes the detector rows ``[lo, hi)`` of every ``(base_ptr, lo, hi)``
+        in ``peers`` into that (peer-memory) band buffer with row pitch ``pitch`` floats (``tsp_fp_push``)."""
+        vp = ctypes.c_void_p
+        n = len(peers)
+        base = (vp * n)(*[vp(b) for b, _, _ in peers])
+        lo = (ctypes.c_int32 * n)(*[int(a) for _, a, _ in peers])
+        hi = (ctypes.c_int32 * n)(*[int(b) for _, _, b in peers])
+        _check(lib().tsp_fp_push(self._handle, vp(vol_ptr), vp(vol_t_ptr), vp(proj_ptr), vp(sub_ptr), vp(mul_ptr), n, base, lo, hi,
+                                 int(pitch), int(device), vp(stream)))
 
     def push_rows(self, jobs, device=0, stream=0):
         """One kernel of strided row copies (``tsp_push_rows``); destinations may be peer memory."""

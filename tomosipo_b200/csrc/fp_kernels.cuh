@@ -18,6 +18,17 @@ namespace tsp {
 constexpr int FP_BU = 32;  // det_u pixels per CTA (= warp width)
 constexpr int FP_BV = 8;   // det_v pixels per CTA
 
+// Multi-GPU row exchange fused into the projector's store (tomosipo_b200/distributed.py, tsp_fp_push): every value of
+// detector row v in [lo[q], hi[q]) is also stored into rank q's band buffer - peer memory, NVLink stores - so the
+// backprojection of the other ranks can start on this rank's angles without a separate exchange pass.
+constexpr int FP_MAX_PEERS = 16;
+struct FPPeers {
+    float *base[FP_MAX_PEERS];  // rank q's band buffer [hi - lo][all angles][U], offset to this rank's first angle
+    int lo[FP_MAX_PEERS], hi[FP_MAX_PEERS];
+    long long pitch;            // floats between rows of the band buffers (all angles * U)
+    int n;                      // 0: single-GPU store
+};
+
 struct FPArgs {
     const float *vol;     // volume in the layout of this group
     long long stride_m;   // elements between consecutive slices
@@ -35,14 +46,20 @@ struct FPArgs {
     // fused SIRT residual (tsp_sirt): when set, the stored value is epi_mul[i] * (value - epi_sub[i])
     const float *epi_sub;
     const float *epi_mul;
+    FPPeers peers;
 };
 
-// The one place a projection value is written: SET, ADD, or the fused SIRT residual.
-__device__ __forceinline__ void fp_store(const FPArgs &P, size_t idx, float val)
+// The one place a projection value is written: SET, ADD, or the fused SIRT residual - and, on a multi-GPU job, the
+// copies of the value in the band buffers of the ranks whose z-slabs read detector row iv.
+__device__ __forceinline__ void fp_store(const FPArgs &P, int iv, int a, int iu, float val)
 {
+    const size_t col = (size_t)a * P.det_u + iu;
+    const size_t idx = (size_t)iv * P.n_angles * P.det_u + col;
     if (P.epi_mul) val = __ldg(P.epi_mul + idx) * (val - __ldg(P.epi_sub + idx));
     float *dst = P.proj + idx;
     *dst = P.additive ? *dst + val : val;
+    for (int q = 0; q < P.peers.n; ++q)
+        if (iv >= P.peers.lo[q] && iv < P.peers.hi[q]) P.peers.base[q][(size_t)(iv - P.peers.lo[q]) * P.peers.pitch + col] = val;
 }
 
 __device__ __forceinline__ int warp_min_i(int v)
@@ -208,7 +225,7 @@ __global__ void __launch_bounds__(FP_BU *FP_BV) fp_kernel(const FPArgs P)
         }
     }
     if (SUPERSAMPLE) sum /= (float)(ss * ss);
-    if (live) fp_store(P, ((size_t)iv * P.n_angles + a) * P.det_u + iu, sum);
+    if (live) fp_store(P, iv, a, iu, sum);
 }
 
 // ---------------------------------------------------------------------------
@@ -356,7 +373,7 @@ __global__ void __launch_bounds__(FP_BU * FP_BV) fp_cols_kernel(const FPArgs P)
     for (int r = 0; r < R; ++r) {
         if (live_u && iv0 + r < P.det_v) {
             const float val = live[r] ? acc[r] * scale[r] : 0.0f;
-            fp_store(P, ((size_t)(iv0 + r) * P.n_angles + a) * P.det_u + iu, val);
+            fp_store(P, iv0 + r, a, iu, val);
         }
     }
 }
@@ -395,7 +412,7 @@ __global__ void __launch_bounds__(256) fp_pool_kernel(const FPArgs P, const floa
         const float *src = fine + ((size_t)(v * d + sv)) * frow + (size_t)a * fu + (size_t)u * d;
         for (int su = 0; su < d; ++su) sum += __ldg(src + su);
     }
-    fp_store(P, ((size_t)(v0 + v) * P.n_angles + a) * P.det_u + u, sum / (float)(d * d));
+    fp_store(P, v0 + v, a, u, sum / (float)(d * d));
 }
 
 }  // namespace tsp

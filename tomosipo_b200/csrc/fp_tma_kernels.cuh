@@ -358,7 +358,7 @@ fp_tma_kernel(const FPTmaArgs A, const __grid_constant__ TensorMapPair tmaps)
                 const float aqr = (r & 1) ? aq2[r / 2].y : aq2[r / 2].x;
                 const float scale = P.sigma_m * sqrtf(1.0f + apr * apr * P.rp2 + aqr * aqr * P.rq2);
                 const float val = ((r & 1) ? acc2[r / 2].y : acc2[r / 2].x) * scale;
-                fp_store(P, ((size_t)(iv0 + r) * P.n_angles + a) * P.det_u + iu, val);
+                fp_store(P, iv0 + r, a, iu, val);
             }
         }
     }

@@ -142,7 +142,6 @@ __global__ void __launch_bounds__(32 * THIN_FP_ANGLES) fp_thin_kernel(const FPAr
         }
     }
     if (!live) return;
-    const size_t pix = ((size_t)iv * P.n_angles + a) * P.det_u + iu;
 #pragma unroll
     for (int j = 0; j < BT; ++j)
         if (j < nb) {
@@ -150,7 +149,7 @@ __global__ void __launch_bounds__(32 * THIN_FP_ANGLES) fp_thin_kernel(const FPAr
             const size_t off = (size_t)(b0 + j) * proj_bstride;
             Q.proj = P.proj + off;
             if (P.epi_mul) { Q.epi_mul = P.epi_mul + off; Q.epi_sub = P.epi_sub + off; }
-            fp_store(Q, pix, acc[j] * scale);
+            fp_store(Q, iv, a, iu, acc[j] * scale);
         }
 }
 

@@ -579,9 +579,12 @@ static int launch_fp_tma_one(dim3 grid, size_t smem, cudaStream_t stream, const 
 
 static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float *proj, int additive,
                      cudaStream_t stream, const float *epi_sub = nullptr, const float *epi_mul = nullptr, int batch = 1,
-                     const float *vol_t_ext = nullptr)  // caller-made (x <-> y)-transposed copy (tsp_transpose_slices)
+                     const float *vol_t_ext = nullptr,  // caller-made (x <-> y)-transposed copy (tsp_transpose_slices)
+                     const FPPeers *peers = nullptr)    // multi-GPU: band buffers the store also writes (tsp_fp_push)
 {
     const tsp_geometry &g = pr->g;
+    if (peers && (batch != 1 || additive || g.detector_supersampling > 1))
+        return fail(TSP_ERR_INVALID, "the fused row exchange takes one plain (SET, no supersampling) forward projection");
     const int n[3] = {g.nx, g.ny, g.nz};
     const size_t nvox = (size_t)g.nx * g.ny * g.nz;
     const size_t npix = (size_t)g.det_rows * g.n_angles * g.det_cols;
@@ -651,6 +654,8 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
         P.det_u = g.det_cols; P.det_v = g.det_rows; P.n_angles = g.n_angles;
         P.additive = additive;
         P.epi_sub = epi_sub; P.epi_mul = epi_mul;
+        if (peers) P.peers = *peers;
+        else P.peers.n = 0;
         P.det_ss = g.detector_supersampling;
         P.sigma_m = (float)pr->sigma[grp.march];
         const double rp = pr->sigma[grp.p_axis] / pr->sigma[grp.march];
@@ -1897,6 +1902,41 @@ extern "C" int tsp_fp_pre_transposed(tsp_projector *pr, const void *vol, const v
     if (int rc = get_device_state(pr, device, &st)) return rc;
     return launch_fp(pr, st, (const float *)vol, (float *)proj, 0, (cudaStream_t)cuda_stream, (const float *)sub, (const float *)mul, 1,
                      (const float *)vol_t);
+}
+
+extern "C" int tsp_fp_push(tsp_projector *pr, const void *vol, const void *vol_t, void *proj, const void *sub, const void *mul,
+                           int n_peers, void *const *peer_base, const int32_t *row_lo, const int32_t *row_hi,
+                           int64_t peer_pitch, int device, void *cuda_stream)
+{
+    if (!pr || !vol || !proj) return fail(TSP_ERR_INVALID, "NULL argument");
+    if ((sub != nullptr) != (mul != nullptr)) return fail(TSP_ERR_INVALID, "sub and mul go together");
+    if (n_peers < 0 || n_peers > FP_MAX_PEERS) return fail(TSP_ERR_INVALID, "%d destinations (at most %d)", n_peers, FP_MAX_PEERS);
+    if (n_peers > 0 && (!peer_base || !row_lo || !row_hi)) return fail(TSP_ERR_INVALID, "NULL argument");
+    const tsp_geometry &g = pr->g;
+    if (n_peers > 0 && peer_pitch < (int64_t)g.n_angles * g.det_cols)
+        return fail(TSP_ERR_INVALID, "band pitch %lld shorter than this projector's %d angles x %d columns", (long long)peer_pitch,
+                    g.n_angles, g.det_cols);
+    FPPeers peers;
+    peers.n = 0;
+    peers.pitch = peer_pitch;
+    for (int q = 0; q < n_peers; ++q) {
+        if (row_hi[q] <= row_lo[q]) continue;  // this destination reads none of the rows
+        if (row_lo[q] < 0 || row_hi[q] > g.det_rows || !peer_base[q])
+            return fail(TSP_ERR_INVALID, "destination %d: rows [%d, %d) of %d, buffer %p", q, row_lo[q], row_hi[q], g.det_rows, peer_base[q]);
+        peers.base[peers.n] = (float *)peer_base[q];
+        peers.lo[peers.n] = row_lo[q];
+        peers.hi[peers.n] = row_hi[q];
+        ++peers.n;
+    }
+    const int ndev = tsp_device_count();
+    if (ndev == 0) return fail(TSP_ERR_CUDA, "no CUDA device available (libtsproj has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(TSP_ERR_INVALID, "device %d out of range [0, %d)", device, ndev);
+    DeviceGuard guard;
+    if (guard.enter(device) != 0) return fail(TSP_ERR_CUDA, "cannot switch to device %d", device);
+    DeviceState *st = nullptr;
+    if (int rc = get_device_state(pr, device, &st)) return rc;
+    return launch_fp(pr, st, (const float *)vol, (float *)proj, 0, (cudaStream_t)cuda_stream, (const float *)sub, (const float *)mul, 1,
+                     (const float *)vol_t, peers.n ? &peers : nullptr);
 }
 
 // -------------------------------------------------------------------- FDK --

@@ -308,14 +308,35 @@ class ShardedOperator:
             self.local.astra_projector.transpose_slices(full.data_ptr(), full_t.data_ptr(), lo, hi, device=full.device.index,
                                                         stream=stream)
 
-    def _fp_local(self, full, full_t, out, y=None, R=None):
-        """``out = A[block] full`` (or ``R * (A full - y)``) from the replicated volume and its transposed copy."""
+    def _lib_fp_ok(self, full, *arrays):
+        """The rank-local operator is the library's and the arrays can go to it by pointer."""
+        proj = getattr(self.local, "astra_projector", None)
+        return (full.is_cuda and proj is not None and hasattr(proj, "fp_pre_transposed")
+                and not getattr(self.local, "additive", False)
+                and all(t.dtype == torch.float32 and t.is_contiguous() for t in (full,) + arrays))
+
+    def _fp_local(self, full, full_t, out, y=None, R=None, turn=None):
+        """``out = A[block] full`` (or ``R * (A full - y)``) from the replicated volume and its transposed copy
+        (None: the library transposes itself if it has to).  ``turn``: band buffer of the peer-memory exchange that the
+        projector's store fills on every rank as it goes (``tsp_fp_push``)."""
         proj = self.local.astra_projector
         stream = torch.cuda.current_stream(full.device).cuda_stream
+        ptr = lambda t: None if t is None else t.data_ptr()
+        P = self._peer
         with torch.cuda.device_of(full):
-            proj.fp_pre_transposed(full.data_ptr(), full_t.data_ptr(), out.data_ptr(),
-                                   None if y is None else y.data_ptr(), None if R is None else R.data_ptr(),
-                                   device=full.device.index, stream=stream)
+            if turn is not None and P and P["fp_push"]:
+                U, a_all = self.proj_shape[2], self.angle_bounds[-1][1]
+                peers = [(P["ptrs"][turn][q] + self.angle_lo * U * 4, a, b) for q, (a, b) in enumerate(self.row_bounds) if b > a]
+                proj.fp_push(full.data_ptr(), ptr(full_t), out.data_ptr(), ptr(y), ptr(R), peers, a_all * U,
+                             device=full.device.index, stream=stream)
+                try:
+                    torch.autograd.graph.increment_version(out)  # written behind torch's back
+                    P["pushed"] = (out, out._version)
+                except RuntimeError:                             # no version counter (inference tensor): not tracked
+                    P["pushed"] = None
+            else:
+                proj.fp_pre_transposed(full.data_ptr(), ptr(full_t), out.data_ptr(), ptr(y), ptr(R),
+                                       device=full.device.index, stream=stream)
         return out
 
     def chunk_operators(self):
@@ -422,7 +443,28 @@ class ShardedOperator:
                 B.peer_free(ptr, dev.index)
             return None
         return {"ptrs": ptrs, "views": views, "turn": 0, "flag": torch.zeros(1, device=dev), "mapped": mapped,
-                "own": [ptr for ptr, _ in own], "device": dev.index}
+                "own": [ptr for ptr, _ in own], "device": dev.index,
+                # the band buffer a forward projection has claimed (on every rank) for the backprojection that follows,
+                # and the (tensor, version) whose rows this rank's projector has already stored there
+                "pending": None, "pushed": None,
+                "fp_push": (not os.environ.get("TSP_SHARD_NO_FP_PUSH")
+                            and hasattr(getattr(self.local, "astra_projector", None), "fp_push"))}
+
+    def _take_turn(self, like, pending=False):
+        """Next band buffer (they alternate) of the peer-memory exchange, or None when it is not in use.  Every rank
+        calls this at the same points of the program, so all ranks agree on the buffer."""
+        if self.bp_exchange != "rows" or self.world == 1:
+            return None
+        if (self._peer is False and like.is_cuda and self._nccl() and not os.environ.get("TSP_SHARD_NO_P2P")
+                and not self._row_split):
+            self._peer = self._peer_setup(like)
+        P = self._peer
+        if not P or not like.is_cuda:
+            return None
+        k = P["turn"]
+        P["turn"] = k ^ 1
+        P["pending"], P["pushed"] = (k if pending else None), None
+        return k
 
     def _exchange_rows_peer(self, y_block):
         """The band of every rank's angle block, stored by the ranks themselves: one kernel of NVLink stores per rank
@@ -432,15 +474,24 @@ class ShardedOperator:
         from . import _backend as B
 
         P = self._peer
-        k = P["turn"]
-        P["turn"] = k ^ 1
-        U = self.proj_shape[2]
-        a_me, a_all = self.angle_hi - self.angle_lo, self.angle_bounds[-1][1]
-        base = y_block.data_ptr()
-        jobs = [(base + a * a_me * U * 4, P["ptrs"][k][q] + self.angle_lo * U * 4, b - a, a_me * U, a_me * U, a_all * U)
-                for q, (a, b) in enumerate(self.row_bounds) if b > a]
-        stream = torch.cuda.current_stream(y_block.device).cuda_stream
-        B.push_rows(jobs, device=P["device"], stream=stream, projector=getattr(self.local, "astra_projector", None))
+        k, pushed = P["pending"], P["pushed"]
+        P["pending"] = P["pushed"] = None
+        if k is None:
+            k = self._take_turn(y_block)
+        if pushed is not None:                             # did this rank's projector store exactly this array's rows?
+            t, version = pushed
+            try:
+                pushed = (t.data_ptr() == y_block.data_ptr() and t.shape == y_block.shape and y_block._version == version)
+            except RuntimeError:                           # no version counter (inference tensor)
+                pushed = False
+        if not pushed:
+            U = self.proj_shape[2]
+            a_me, a_all = self.angle_hi - self.angle_lo, self.angle_bounds[-1][1]
+            base = y_block.data_ptr()
+            jobs = [(base + a * a_me * U * 4, P["ptrs"][k][q] + self.angle_lo * U * 4, b - a, a_me * U, a_me * U, a_all * U)
+                    for q, (a, b) in enumerate(self.row_bounds) if b > a]
+            stream = torch.cuda.current_stream(y_block.device).cuda_stream
+            B.push_rows(jobs, device=P["device"], stream=stream, projector=getattr(self.local, "astra_projector", None))
         dist.all_reduce(P["flag"], group=self.group)
         return P["views"][k]
 
@@ -461,10 +512,11 @@ class ShardedOperator:
         """``[rows of this rank's band, angles, U]`` from every rank's angle block: rank ``q`` receives rows
         ``row_bounds[q]`` of each block (contiguous: rows are the outermost axis) and interleaves the blocks by angle
         (all angles, or all but the rank's own block)."""
-        if (with_own and self._peer is False and y_block.is_cuda and self._nccl() and y_block.dtype == torch.float32
-                and not os.environ.get("TSP_SHARD_NO_P2P")):
-            self._peer = self._peer_setup(y_block)
-        if with_own and self._peer and y_block.is_cuda and y_block.dtype == torch.float32 and y_block.is_contiguous():
+        if with_own and y_block.is_cuda and self._peer is False:
+            self._take_turn(y_block)                       # sets the peer-memory exchange up (the turn itself is unused)
+        if with_own and self._peer and y_block.is_cuda:
+            if y_block.dtype != torch.float32 or not y_block.is_contiguous():
+                y_block = y_block.to(torch.float32).contiguous()
             return self._exchange_rows_peer(y_block)
         lo, hi = self.row_bounds[self.rank]
         U = self.proj_shape[2]
@@ -563,12 +615,17 @@ class ShardedOperator:
         # rest of the all-gather hides behind their kernels, was built and measured in round 2: the blocks' extra
         # launches, wave tails and per-block transposes cost more than the all-gather they hide - 24.5 vs 22.5 ms at
         # N = 2, 6.56 vs 6.29 ms at N = 8, cfg 3 - and it was dropped.)
-        full_t = self._transposed_volume(x_slab) if (out.is_contiguous() and out.dtype == torch.float32) else None
+        lib_ok = self._lib_fp_ok(full, out)
+        full_t = self._transposed_volume(x_slab) if lib_ok else None
         compute, comm = self._streams(x_slab)
+        turn = self._take_turn(x_slab, pending=True)       # peer-memory exchange: the band buffer this projection fills
         if full_t is None or comm is None:
             for c in range(self.chunks):
                 self._all_gather_chunk(full, x_slab, c)
-            self.local(full[: self.vol_shape[0]], out=out)
+            if lib_ok:
+                self._fp_local(full, None, out, turn=turn)
+            else:
+                self.local(full[: self.vol_shape[0]], out=out)
             return out
         # x-marching ranks: gather chunk by chunk on the communication stream and transpose every chunk as it lands,
         # behind the all-gather of the next one; the forward projection then reads the finished copy
@@ -581,7 +638,7 @@ class ShardedOperator:
             compute.wait_event(ev)
             self._transpose_chunk(full, full_t, c)
         x_slab.record_stream(comm)
-        self._fp_local(full, full_t, out)
+        self._fp_local(full, full_t, out, turn=turn)
         return out
 
     def _bp(self, y_block, out=None):
@@ -605,9 +662,10 @@ class ShardedOperator:
         """``out = R * (A[angle block] x_full - y)`` for a replicated volume: in the projector's
         store when the rank-local operator is the library's (CUDA), else the explicit three passes.
         ``x_full_t``: the caller-maintained transposed copy of ``x_full`` (see :meth:`_transposed_volume`)."""
+        turn = self._take_turn(x_full, pending=True) if self.world > 1 else None
+        if self.world > 1 and self._lib_fp_ok(x_full, y, R, out):
+            return self._fp_local(x_full, x_full_t, out, y, R, turn=turn)
         proj = getattr(self.local, "astra_projector", None)
-        if x_full_t is not None and all(t.dtype == torch.float32 and t.is_contiguous() for t in (y, R, out)):
-            return self._fp_local(x_full, x_full_t, out, y, R)
         if (proj is not None and x_full.is_cuda and hasattr(proj, "project_fused") and not self.local.additive
                 and all(t.dtype == torch.float32 and t.is_contiguous() for t in (x_full, y, R, out))):
             from . import _backend
