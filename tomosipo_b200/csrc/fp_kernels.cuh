@@ -51,10 +51,11 @@ struct FPArgs {
 
 // The one place a projection value is written: SET, ADD, or the fused SIRT residual - and, on a multi-GPU job, the
 // copies of the value in the band buffers of the ranks whose z-slabs read detector row iv.
-__device__ __forceinline__ void fp_store(const FPArgs &P, int iv, int a, int iu, float val)
+// `batch_off`: element offset of a batch item in proj / epi_sub / epi_mul (thin kernels); the peers take batch item 0 only.
+__device__ __forceinline__ void fp_store(const FPArgs &P, int iv, int a, int iu, float val, size_t batch_off = 0)
 {
     const size_t col = (size_t)a * P.det_u + iu;
-    const size_t idx = (size_t)iv * P.n_angles * P.det_u + col;
+    const size_t idx = batch_off + (size_t)iv * P.n_angles * P.det_u + col;
     if (P.epi_mul) val = __ldg(P.epi_mul + idx) * (val - __ldg(P.epi_sub + idx));
     float *dst = P.proj + idx;
     *dst = P.additive ? *dst + val : val;

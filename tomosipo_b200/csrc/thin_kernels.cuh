@@ -144,13 +144,7 @@ __global__ void __launch_bounds__(32 * THIN_FP_ANGLES) fp_thin_kernel(const FPAr
     if (!live) return;
 #pragma unroll
     for (int j = 0; j < BT; ++j)
-        if (j < nb) {
-            FPArgs Q = P;
-            const size_t off = (size_t)(b0 + j) * proj_bstride;
-            Q.proj = P.proj + off;
-            if (P.epi_mul) { Q.epi_mul = P.epi_mul + off; Q.epi_sub = P.epi_sub + off; }
-            fp_store(Q, iv, a, iu, acc[j] * scale);
-        }
+        if (j < nb) fp_store(P, iv, a, iu, acc[j] * scale, (size_t)(b0 + j) * proj_bstride);
 }
 
 // grid: (x tiles of 32, y tiles of 8, batch groups); every thread owns one (x, y) column of

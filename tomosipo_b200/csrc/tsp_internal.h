@@ -69,7 +69,8 @@ struct DeviceState {
     cudaMemPool_t pool = nullptr;
     bool owns_pool = true;      // false: the pool belongs to the projector this one is a sub-projector of
     DeviceState *pool_st = nullptr;  // ... and this is that projector's state (its release threshold is the one that counts)
-    size_t pool_keep = 0;       // current release threshold
+    size_t pool_keep = 0;       // bytes this projector wants cached between calls (the threshold adds slack, see pool_keep_at_least)
+    size_t pool_extra = 0;      // owner only: what its sub-projectors want on top (sum of their pool_keep)
     size_t pool_keep_base = 0;  // the part kept for device-array calls (transposed-volume scratch)
 };
 

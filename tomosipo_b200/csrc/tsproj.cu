@@ -531,19 +531,29 @@ static cudaError_t pool_alloc(DeviceState *st, void **p, size_t bytes, cudaStrea
 // so that an iterative loop over host arrays (the README SIRT of the reference) does not map and unmap gigabytes per
 // call (measured: 1807 -> 1127 GUPS end to end without this).  The bound is what this projector itself needs for one
 // call; tsp_projector_destroy gives everything back.
-static void pool_keep_at_least(DeviceState *st, size_t bytes)
+static void pool_set_threshold(DeviceState *owner)
 {
-    if (st->pool_st) {  // a sub-projector: its needs come on top of what the owner keeps for itself
-        pool_keep_at_least(st->pool_st, st->pool_st->pool_keep_base + bytes);
-        return;
-    }
-    if (!st->pool || bytes <= st->pool_keep) return;
     // the pool reserves whole 2 MB granules per allocation: a threshold equal to the bytes requested is exceeded by the
     // rounding, and the excess block would be unmapped and mapped again on every call (measured: 1.8 instead of 0.65 ms
     // per 18 MB host-array call, r02 GPU call 10) - keep a quarter plus 32 MB of slack
-    uint64_t keep = (uint64_t)bytes + bytes / 4 + ((uint64_t)32 << 20);
-    if (cudaMemPoolSetAttribute(st->pool, cudaMemPoolAttrReleaseThreshold, &keep) == cudaSuccess) st->pool_keep = bytes;
-    else cudaGetLastError();
+    const uint64_t total = (uint64_t)owner->pool_keep + owner->pool_extra;
+    uint64_t keep = total + total / 4 + ((uint64_t)32 << 20);
+    if (cudaMemPoolSetAttribute(owner->pool, cudaMemPoolAttrReleaseThreshold, &keep) != cudaSuccess) cudaGetLastError();
+}
+
+static void pool_keep_at_least(DeviceState *st, size_t bytes)
+{
+    if (bytes <= st->pool_keep) return;
+    if (st->pool_st) {  // a sub-projector: its scratch comes on top of what the owner and the other sub-projectors keep
+        if (!st->pool_st->pool) return;
+        st->pool_st->pool_extra += bytes - st->pool_keep;
+        st->pool_keep = bytes;
+        pool_set_threshold(st->pool_st);
+        return;
+    }
+    if (!st->pool) return;
+    st->pool_keep = bytes;
+    pool_set_threshold(st);
 }
 
 // Per-call scratch from the projector's private pool, released (stream-ordered) on every exit path.
