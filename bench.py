@@ -253,7 +253,9 @@ def sharded_parity_check(ts, ShardedOperator, dev, world):
     e_bp = torch.linalg.vector_norm(xb_slab - xb_ref) / torch.linalg.vector_norm(xb_ref)
     t = torch.stack([e_fp, e_bp]).float()
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return {"fp": float(t[0]), "bp": float(t[1]), "problem": f"cone {n}^3 x {na} angles x {n}x{3 * n // 2}, {S.chunks} z-chunks, bp_exchange={S.bp_exchange}",
+    mode = S.bp_exchange
+    S.close()                                                # band buffers of the row exchange (collective)
+    return {"fp": float(t[0]), "bp": float(t[1]), "problem": f"cone {n}^3 x {na} angles x {n}x{3 * n // 2}, {S.chunks} z-chunks, bp_exchange={mode}",
             "ranks": world}
 
 

@@ -495,8 +495,24 @@ class ShardedOperator:
         dist.all_reduce(P["flag"], group=self.group)
         return P["views"][k]
 
+    def __del__(self):
+        # not collective: only this process's mappings of the peers' buffers can go; the own buffers must outlive the
+        # peers' mappings and stay until close() or process exit
+        P = getattr(self, "_peer", None)
+        if P and P.get("mapped"):
+            try:
+                from . import _backend as B
+
+                torch.cuda.synchronize(P["device"])
+                for ptr in P["mapped"]:
+                    B.peer_close(ptr, P["device"])
+                P["mapped"] = []
+            except Exception:
+                pass
+
     def close(self):
-        """Unmap the peers' band buffers and release the own ones (collective; optional - process exit does the same)."""
+        """Unmap the peers' band buffers and release the own ones (collective: every rank calls it; without it the
+        own buffers live until the process exits)."""
         P, self._peer = self._peer, None
         if P:
             from . import _backend as B
