@@ -431,7 +431,7 @@ class ShardedOperator:
         views = []
         if ok:
             views = [torch.as_tensor(B.DeviceBuffer(ptr, shape), device=dev) for ptr, _ in own]
-            if any(v.data_ptr() != ptr or v.device != dev for v, (ptr, _) in zip(views, own)):
+            if any(v.numel() and (v.data_ptr() != ptr or v.device != dev) for v, (ptr, _) in zip(views, own)):
                 ok = 0.0                                   # torch copied instead of wrapping the buffer
         flag = torch.tensor([ok], device=dev)
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
@@ -447,7 +447,7 @@ class ShardedOperator:
                 # the band buffer a forward projection has claimed (on every rank) for the backprojection that follows,
                 # and the (tensor, version) whose rows this rank's projector has already stored there
                 "pending": None, "pushed": None,
-                "fp_push": (not os.environ.get("TSP_SHARD_NO_FP_PUSH")
+                "fp_push": (not os.environ.get("TSP_SHARD_NO_FP_PUSH") and self.world <= 16      # FP_MAX_PEERS
                             and hasattr(getattr(self.local, "astra_projector", None), "fp_push"))}
 
     def _take_turn(self, like, pending=False):
