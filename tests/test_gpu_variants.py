@@ -46,6 +46,8 @@ FP_VARIANTS = [
     {"TSP_FP_BOX_SHRINK": 3},             # undersized box: some slices take the "unfit" global path
     {"TSP_FP_BOX_SHRINK": 40},            # box far too small: every slice unfit
     {"TSP_FP_STAGES": 2},
+    {"TSP_FP_SEGMENTS": 2},               # marching axis in segments, later ones accumulate (large volumes: L2-sized slabs)
+    {"TSP_FP_SEGMENTS": 3},
 ]
 BP_VARIANTS = [{}, {"TSP_BP_NO_TMA": 1}, {"TSP_BP_ZPT": 1}, {"TSP_BP_ZPT": 4}, {"TSP_BP_ZPT": 8}, {"TSP_BP_ZPT": 16},
                {"TSP_BP_ZPT": 32}, {"TSP_BP_ZPT": 64}, {"TSP_BP_ROWS": 2}]
@@ -210,6 +212,35 @@ def test_project_fused_halves_match_explicit_passes():
         P.project_fused(B.FP, x.data_ptr(), r.data_ptr(), None, R.data_ptr(), device=0, stream=s)
     with pytest.raises(ValueError):
         P.project_fused(B.BP, x.data_ptr(), r.data_ptr(), y.data_ptr(), C.data_ptr(), device=0, stream=s)
+
+
+def test_segmented_fp_keeps_add_mode_and_the_fused_residual():
+    """A forward projection split into segments of the marching axis (TSP_FP_SEGMENTS; automatic for volumes whose
+    per-row-tile slab outgrows L2): ADD adds to the caller's data once, the fused residual is formed from the whole sum."""
+    import torch
+    import tomosipo_b200 as ts
+    from tomosipo_b200 import _backend as B
+
+    vg = ts.volume(shape=(40, 72, 68), size=(1.0, 1.8, 1.7))
+    pg = ts.cone(angles=23, shape=(40, 96), size=(2.0, 4.8), src_orig_dist=5, src_det_dist=8)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    s = torch.cuda.current_stream().cuda_stream
+    A1 = ts.operator(vg, pg)
+    x = torch.rand(A1.domain_shape, device="cuda", generator=g)
+    y = torch.rand(A1.range_shape, device="cuda", generator=g)
+    R = torch.rand(A1.range_shape, device="cuda", generator=g)
+    ref = A1(x)
+    with env(TSP_FP_SEGMENTS=3):
+        A, Aadd = ts.operator(vg, pg), ts.operator(vg, pg, additive=True)
+        n0 = A.astra_projector.info().kernel_launches
+        torch.testing.assert_close(A(x), ref, rtol=1e-5, atol=1e-5 * float(ref.max()))
+        assert A.astra_projector.info().kernel_launches - n0 >= 3          # one launch per segment (and group)
+        acc = y.clone()
+        Aadd(x, out=acc)
+        torch.testing.assert_close(acc, y + ref, rtol=1e-5, atol=1e-5 * float(ref.max()))
+        r = torch.empty_like(y)
+        A.astra_projector.project_fused(B.FP, x.data_ptr(), r.data_ptr(), y.data_ptr(), R.data_ptr(), device=0, stream=s)
+        torch.testing.assert_close(r, R * (ref - y), rtol=1e-5, atol=1e-5 * float(ref.max()))
 
 
 @pytest.mark.parametrize("kindname", ["par_slab", "cone_thin"])

@@ -38,7 +38,7 @@ struct FPArgs {
     const int *list;      // angle ids of this group
     float *proj;
     int det_u, det_v, n_angles;
-    int additive;
+    int additive;         // 0: SET, 1: ADD to the output, 2: continue a segmented projection (sum, then epilogue, then SET)
     int det_ss;
     float sigma_m;        // voxel size along the march axis
     float rp2, rq2;       // (sigma_p / sigma_m)^2, (sigma_q / sigma_m)^2
@@ -56,9 +56,10 @@ __device__ __forceinline__ void fp_store(const FPArgs &P, int iv, int a, int iu,
 {
     const size_t col = (size_t)a * P.det_u + iu;
     const size_t idx = batch_off + (size_t)iv * P.n_angles * P.det_u + col;
-    if (P.epi_mul) val = __ldg(P.epi_mul + idx) * (val - __ldg(P.epi_sub + idx));
     float *dst = P.proj + idx;
-    *dst = P.additive ? *dst + val : val;
+    if (P.additive == 2) val += *dst;  // a later segment of a segmented projection: the sum so far is in the output
+    if (P.epi_mul) val = __ldg(P.epi_mul + idx) * (val - __ldg(P.epi_sub + idx));
+    *dst = P.additive == 1 ? *dst + val : val;
     for (int q = 0; q < P.peers.n; ++q)
         if (iv >= P.peers.lo[q] && iv < P.peers.hi[q]) P.peers.base[q][(size_t)(iv - P.peers.lo[q]) * P.peers.pitch + col] = val;
 }

@@ -587,6 +587,8 @@ static int launch_fp_tma_one(dim3 grid, size_t smem, cudaStream_t stream, const 
     return TSP_OK;
 }
 
+static inline bool last_seg(int seg, int segments) { return seg == segments - 1; }
+
 static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float *proj, int additive,
                      cudaStream_t stream, const float *epi_sub = nullptr, const float *epi_mul = nullptr, int batch = 1,
                      const float *vol_t_ext = nullptr,  // caller-made (x <-> y)-transposed copy (tsp_transpose_slices)
@@ -768,16 +770,33 @@ static int launch_fp(tsp_projector *pr, DeviceState *st, const float *vol, float
                 const size_t smem = 128 + (size_t)T.stages * (T.stage_bytes + 24) + 16;
                 dim3 tgrid((g.det_cols + FPT_TU - 1) / FPT_TU, (unsigned)(grp.pairs.size() / 2),
                            (g.det_rows + 4 * R - 1) / (4 * R));
-                int rc;
+                // segments of the marching axis (FPTmaArgs::m_begin): as many as keep the slab one detector row tile
+                // reads - every in-plane position x the staged box's q rows - within 72 MB (cfg 3: 53 MB, one segment,
+                // 97.8 % L2 hits; cfg 4: 210 MB -> 3 segments: 811 / 705 / 697 / 716 / 766 ms with 1 / 2 / 3 / 4 / 6, r02 GPU call 39)
+                const double slab_bytes = (double)P.n_p * P.n_m * box_h * 4.0;
+                int segments = (int)std::min(8.0, std::ceil(slab_bytes / (72.0 * 1024 * 1024)));
+                if (const char *e = getenv("TSP_FP_SEGMENTS")) segments = atoi(e);
+                segments = std::max(1, std::min(segments, std::max(1, P.n_m / 32)));
+                for (int seg = 0; seg < segments; ++seg) {
+                    T.m_begin = (int)((long long)P.n_m * seg / segments) & ~1;  // even: stages of two slices stay inside
+                    T.m_end = last_seg(seg, segments) ? P.n_m : (int)((long long)P.n_m * (seg + 1) / segments) & ~1;
+                    // the epilogue and the peers' copies belong to the last segment, which holds the whole sum
+                    const bool last = seg == segments - 1;
+                    T.a.additive = seg == 0 ? P.additive : (P.additive == 1 ? 1 : 2);
+                    T.a.epi_sub = last ? P.epi_sub : nullptr;
+                    T.a.epi_mul = last ? P.epi_mul : nullptr;
+                    T.a.peers.n = last ? P.peers.n : 0;
+                    int rc;
 #define TSP_FPT_S(C, L, S) (R == 8 ? launch_fp_tma_one<C, L, 8, S>(tgrid, smem, stream, T, slot) \
                                    : launch_fp_tma_one<C, L, 4, S>(tgrid, smem, stream, T, slot))
 #define TSP_FPT(C, L) (sps == 2 ? TSP_FPT_S(C, L, 2) : TSP_FPT_S(C, L, 1))
-                if (cone) rc = grp.columns ? TSP_FPT(true, true) : TSP_FPT(true, false);
-                else rc = grp.columns ? TSP_FPT(false, true) : TSP_FPT(false, false);
+                    if (cone) rc = grp.columns ? TSP_FPT(true, true) : TSP_FPT(true, false);
+                    else rc = grp.columns ? TSP_FPT(false, true) : TSP_FPT(false, false);
 #undef TSP_FPT
 #undef TSP_FPT_S
-                if (rc) return rc;
-                ++pr->launches;
+                    if (rc) return rc;
+                    ++pr->launches;
+                }
                 used_tma = 1;
                 continue;
             }
