@@ -171,6 +171,14 @@ def test_slab_row_bounds_and_cropped_geometry(monkeypatch):
                 a, b = pg.to_vec().project_point(tuple(p)), sub_pg.project_point(tuple(p))
                 np.testing.assert_allclose(a[:, 0] + V / 2.0 - lo, b[:, 0] + (hi - lo) / 2.0, atol=1e-9)
                 np.testing.assert_allclose(a[:, 1], b[:, 1], atol=1e-9)
+    # angle subsets (the opt-in two-launch variant back-projects the own block and the others separately)
+    pg = ts.cone(angles=11, shape=(40, 30), size=(6.0, 4.5), src_orig_dist=4, src_det_dist=7).to_vec()
+    pick = np.array([7, 8, 0, 3])
+    sub_pg = crop_detector_rows(pg, 5, 29, pick)
+    assert sub_pg.num_angles == 4 and tuple(sub_pg.det_shape) == (24, 30)
+    p = (0.3, -0.2, 0.5)
+    np.testing.assert_allclose(pg.project_point(p)[pick, 0] + 20.0 - 5, sub_pg.project_point(p)[:, 0] + 12.0, atol=1e-9)
+    np.testing.assert_allclose(pg.project_point(p)[pick, 1], sub_pg.project_point(p)[:, 1], atol=1e-9)
     monkeypatch.delenv("TSP_SHARD_BP", raising=False)
     big = ts.volume(shape=(64, 64, 64))
     circ = ts.cone(angles=96, shape=(64, 96), size=(64 * 1.5, 96 * 1.5), src_orig_dist=256, src_det_dist=384)
